@@ -1,0 +1,440 @@
+// capi.cu -- the C ABI (include/sss_b200.h): context, argument checking, device-resident entry
+// points, and the host-buffer entry points that the C++ drop-in layer (include/simd_scan.hpp)
+// calls.  Every CUDA return code is checked and surfaced as an int status; there is no CPU path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/sss_b200.h"
+#include "kernels.h"
+
+using namespace sss;
+
+namespace {
+
+constexpr int kSlots = 3;                       // host<->device staging ring depth
+constexpr uint64_t kChunkBytes = 64ull << 20;   // target bytes per staged chunk (larger of in/out)
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    void* d_in = nullptr;
+    size_t in_cap = 0;
+    void* d_out = nullptr;
+    size_t out_cap = 0;
+};
+
+inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? SSS_OK : SSS_ERR_CUDA_BASE + (int)e; }
+
+#define SSS_CK(expr)                                       \
+    do {                                                   \
+        cudaError_t _e = (expr);                           \
+        if (_e != cudaSuccess) return cuda_status(_e);     \
+    } while (0)
+
+#define SSS_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != SSS_OK) return _s;  \
+    } while (0)
+
+}  // namespace
+
+struct sss_ctx {
+    Device dev;
+    Slot slots[kSlots];
+    uint32_t* d_lo = nullptr;  // SSS_MAX_PREDICATES each, for the host entry points
+    uint32_t* d_hi = nullptr;
+    unsigned long long* d_counts = nullptr;  // SSS_MAX_PREDICATES + 1
+    void* d_ws = nullptr;                    // positions workspace
+    size_t ws_cap = 0;
+};
+
+namespace {
+
+int grow(void** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return SSS_OK;
+    if (*p) SSS_CK(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    SSS_CK(cudaMalloc(p, need));
+    *cap = need;
+    return SSS_OK;
+}
+
+int check_common(const sss_ctx* ctx, const void* packed, int w)
+{
+    if (ctx == nullptr || packed == nullptr) return SSS_ERR_INVALID_ARG;
+    if (w < 1 || w > 32) return SSS_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(packed) & 15) return SSS_ERR_INVALID_ARG;
+    return SSS_OK;
+}
+
+int check_k(int K) { return (K < 1 || K > SSS_MAX_PREDICATES) ? SSS_ERR_INVALID_ARG : SSS_OK; }
+
+uint64_t out_bytes_for(uint64_t n, int granule) { return granule == 32 ? 4 * ((n + 31) / 32) : (n + 7) / 8; }
+uint64_t eval_codes_for(uint64_t n, int granule) { return granule <= 1 ? n : round_up_u64(n, (uint64_t)granule); }
+
+// codes per staged chunk: a multiple of 1024 codes (=> whole words in, whole words out, 16-byte
+// aligned packed offsets for every width)
+uint64_t chunk_codes(double in_bytes_per_code, double out_bytes_per_code)
+{
+    const double per = std::max(in_bytes_per_code, out_bytes_per_code);
+    uint64_t c = (uint64_t)((double)kChunkBytes / per);
+    c = c / 1024 * 1024;
+    return c < 1024 ? 1024 : c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sss_version(void) { return 100; }
+
+const char* sss_error_string(int status)
+{
+    switch (status) {
+        case SSS_OK: return "ok";
+        case SSS_ERR_INVALID_ARG: return "invalid argument";
+        case SSS_ERR_UNSUPPORTED: return "unsupported";
+        case SSS_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    }
+    if (status >= SSS_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(status - SSS_ERR_CUDA_BASE));
+    return "unknown status";
+}
+
+int sss_ctx_create(int device, sss_ctx** out)
+{
+    if (out == nullptr) return SSS_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        return SSS_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SSS_CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return SSS_ERR_UNSUPPORTED;  // kernels are sm_100a only
+    sss_ctx* ctx = new (std::nothrow) sss_ctx();
+    if (ctx == nullptr) return SSS_ERR_CUDA_BASE + (int)cudaErrorMemoryAllocation;
+    ctx->dev = Device{device, prop.multiProcessorCount, (int)prop.sharedMemPerBlockOptin};
+    for (auto& s : ctx->slots) {
+        cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            sss_ctx_destroy(ctx);
+            return cuda_status(e);
+        }
+    }
+    cudaError_t e = cudaMalloc(&ctx->d_lo, SSS_MAX_PREDICATES * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_hi, SSS_MAX_PREDICATES * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counts, (SSS_MAX_PREDICATES + 1) * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        sss_ctx_destroy(ctx);
+        return cuda_status(e);
+    }
+    *out = ctx;
+    return SSS_OK;
+}
+
+int sss_ctx_destroy(sss_ctx* ctx)
+{
+    if (ctx == nullptr) return SSS_OK;
+    cudaSetDevice(ctx->dev.ordinal);
+    for (auto& s : ctx->slots) {
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+    }
+    if (ctx->d_lo) cudaFree(ctx->d_lo);
+    if (ctx->d_hi) cudaFree(ctx->d_hi);
+    if (ctx->d_counts) cudaFree(ctx->d_counts);
+    if (ctx->d_ws) cudaFree(ctx->d_ws);
+    delete ctx;
+    return SSS_OK;
+}
+
+int sss_ctx_sm_count(const sss_ctx* ctx) { return ctx ? ctx->dev.sm_count : 0; }
+
+size_t sss_packed_bytes(uint64_t n, int w) { return (size_t)(packed_payload_bytes(n, w) + 256); }
+size_t sss_unpack_bytes(uint64_t n) { return (size_t)(n * 4 + 32); }
+size_t sss_bitvec_bytes(uint64_t n) { return (size_t)((n + 7) / 8 + 32); }
+
+// ---- device-resident entry points ----------------------------------------------------------
+
+int sss_pack(sss_ctx* ctx, const uint32_t* d_codes, uint64_t n, int w, void* d_packed, void* stream)
+{
+    SSS_TRY(check_common(ctx, d_packed, w));
+    if (d_codes == nullptr && n != 0) return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    const size_t bytes = sss_packed_bytes(n, w);
+    const uint64_t words = bytes / 4;
+    auto st = static_cast<cudaStream_t>(stream);
+    if (bytes % 4) SSS_CK(cudaMemsetAsync(static_cast<uint8_t*>(d_packed) + words * 4, 0, bytes % 4, st));
+    return cuda_status(launch_pack(ctx->dev, d_codes, n, w, static_cast<uint32_t*>(d_packed), words, st));
+}
+
+int sss_generate_packed(sss_ctx* ctx, void* d_packed, uint64_t n, int w, uint64_t seed, uint64_t first_index,
+                        void* stream)
+{
+    SSS_TRY(check_common(ctx, d_packed, w));
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    const size_t bytes = sss_packed_bytes(n, w);
+    const uint64_t words = bytes / 4;
+    auto st = static_cast<cudaStream_t>(stream);
+    if (bytes % 4) SSS_CK(cudaMemsetAsync(static_cast<uint8_t*>(d_packed) + words * 4, 0, bytes % 4, st));
+    return cuda_status(
+        launch_generate_packed(ctx->dev, static_cast<uint32_t*>(d_packed), words, n, w, seed, first_index, st));
+}
+
+int sss_unpack(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, int32_t* d_out, void* stream)
+{
+    SSS_TRY(check_common(ctx, d_packed, w));
+    if (d_out == nullptr || (reinterpret_cast<uintptr_t>(d_out) & 15)) return SSS_ERR_INVALID_ARG;
+    if (n == 0) return SSS_OK;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    return cuda_status(launch_unpack(ctx->dev, d_packed, n, w, d_out, static_cast<cudaStream_t>(stream)));
+}
+
+static int scan_range_impl(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32_t lo, uint32_t hi,
+                           void* d_bitvec, unsigned long long* d_count, bool zero_count, cudaStream_t st)
+{
+    if (d_count && zero_count) SSS_CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+    if (n == 0) return SSS_OK;
+    const AlignedRange r = aligned_range(w, lo, hi);
+    if (r.empty) return cuda_status(cudaMemsetAsync(d_bitvec, 0, 4 * ((n + 31) / 32), st));
+    return cuda_status(launch_scan_range(ctx->dev, d_packed, n, w, r, static_cast<uint32_t*>(d_bitvec), d_count, st));
+}
+
+int sss_scan_range(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32_t lo, uint32_t hi, void* d_bitvec,
+                   uint64_t* d_count, void* stream)
+{
+    SSS_TRY(check_common(ctx, d_packed, w));
+    if (d_bitvec == nullptr || (reinterpret_cast<uintptr_t>(d_bitvec) & 3)) return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    return scan_range_impl(ctx, d_packed, n, w, lo, hi, d_bitvec, reinterpret_cast<unsigned long long*>(d_count), true,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int sss_positions(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base, uint64_t* d_positions,
+                  uint64_t capacity, uint64_t* d_num, void* stream)
+{
+    if (ctx == nullptr || d_bitvec == nullptr || (reinterpret_cast<uintptr_t>(d_bitvec) & 3)) return SSS_ERR_INVALID_ARG;
+    if (d_positions == nullptr && capacity != 0) return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    auto st = static_cast<cudaStream_t>(stream);
+    const size_t need = positions_workspace_bytes(n);
+    if (ctx->ws_cap < need) {
+        // growing the workspace synchronises; callers that time this path warm it up first
+        SSS_CK(cudaStreamSynchronize(st));
+        SSS_TRY(grow(&ctx->d_ws, &ctx->ws_cap, need + need / 4));
+    }
+    return cuda_status(launch_positions(ctx->dev, static_cast<const uint32_t*>(d_bitvec), n, base,
+                                        reinterpret_cast<unsigned long long*>(d_positions), capacity,
+                                        reinterpret_cast<unsigned long long*>(d_num), ctx->d_ws, st));
+}
+
+static int shared_impl(sss_ctx* ctx, bool linear, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo,
+                       const uint32_t* d_hi, int K, void* d_out, uint64_t stride_bytes, unsigned long long* d_counts,
+                       bool zero_counts, cudaStream_t st)
+{
+    if (d_counts && zero_counts) SSS_CK(cudaMemsetAsync(d_counts, 0, (size_t)K * sizeof(unsigned long long), st));
+    if (n == 0) return SSS_OK;
+    if (linear)
+        return cuda_status(
+            launch_shared_scan_linear(ctx->dev, d_packed, n, w, d_lo, d_hi, K, static_cast<uint8_t*>(d_out), d_counts, st));
+    return cuda_status(launch_shared_scan(ctx->dev, d_packed, n, w, d_lo, d_hi, K, static_cast<uint32_t*>(d_out),
+                                          stride_bytes / 4, d_counts, st));
+}
+
+int sss_shared_scan(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo, const uint32_t* d_hi,
+                    int K, void* d_bitvecs, uint64_t stride_bytes, uint64_t* d_counts, void* stream)
+{
+    SSS_TRY(check_common(ctx, d_packed, w));
+    SSS_TRY(check_k(K));
+    if (d_lo == nullptr || d_hi == nullptr || d_bitvecs == nullptr) return SSS_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_bitvecs) & 3) || (stride_bytes & 3) || stride_bytes < 4 * ((n + 31) / 32))
+        return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    return shared_impl(ctx, false, d_packed, n, w, d_lo, d_hi, K, d_bitvecs, stride_bytes,
+                       reinterpret_cast<unsigned long long*>(d_counts), true, static_cast<cudaStream_t>(stream));
+}
+
+int sss_shared_scan_linear(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo,
+                           const uint32_t* d_hi, int K, void* d_out, uint64_t* d_counts, void* stream)
+{
+    SSS_TRY(check_common(ctx, d_packed, w));
+    SSS_TRY(check_k(K));
+    if (d_lo == nullptr || d_hi == nullptr || d_out == nullptr) return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    return shared_impl(ctx, true, d_packed, n, w, d_lo, d_hi, K, d_out, 0,
+                       reinterpret_cast<unsigned long long*>(d_counts), true, static_cast<cudaStream_t>(stream));
+}
+
+// ---- host-buffer entry points ----------------------------------------------------------------
+//
+// The column is cut into chunks of a multiple of 1024 codes.  Chunk c uses staging slot c % 3
+// (own stream, own device buffers): H2D copy, kernel and D2H copy are enqueued on that stream, so
+// the copies of neighbouring chunks overlap the kernel and a slot is never reused before its
+// previous D2H has finished (same-stream ordering).
+
+int sss_host_unpack(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, int32_t* h_out)
+{
+    if (ctx == nullptr || h_packed == nullptr || h_out == nullptr || w < 1 || w > 32) return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    const uint64_t C = chunk_codes(w / 8.0, 4.0);
+    int slot = 0;
+    for (uint64_t first = 0; first < n; first += C, slot = (slot + 1) % kSlots) {
+        Slot& s = ctx->slots[slot];
+        const uint64_t cnt = std::min(C, n - first);
+        const uint64_t in_bytes = round_up_u64(packed_payload_bytes(cnt, w), 16);
+        SSS_TRY(grow(&s.d_in, &s.in_cap, round_up_u64(packed_payload_bytes(C, w), 16) + 16));
+        SSS_TRY(grow(&s.d_out, &s.out_cap, C * 4));
+        const uint8_t* src = static_cast<const uint8_t*>(h_packed) + first * (uint64_t)w / 8;
+        SSS_CK(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
+        SSS_CK(launch_unpack(ctx->dev, s.d_in, cnt, w, static_cast<int32_t*>(s.d_out), s.stream));
+        SSS_CK(cudaMemcpyAsync(h_out + first, s.d_out, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
+    return SSS_OK;
+}
+
+int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, uint32_t lo, uint32_t hi,
+                        int tail_granule, void* h_bitvec, uint64_t* h_count)
+{
+    if (ctx == nullptr || h_packed == nullptr || h_bitvec == nullptr || w < 1 || w > 32) return SSS_ERR_INVALID_ARG;
+    if (tail_granule != 1 && tail_granule != 8 && tail_granule != 32) return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    const uint64_t n_eval = eval_codes_for(n, tail_granule);
+    const uint64_t out_total = out_bytes_for(n, tail_granule);
+    const uint64_t C = chunk_codes(w / 8.0, 1 / 8.0);
+    SSS_CK(cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned long long), ctx->slots[0].stream));
+    SSS_CK(cudaStreamSynchronize(ctx->slots[0].stream));
+    int slot = 0;
+    for (uint64_t first = 0; first < n_eval; first += C, slot = (slot + 1) % kSlots) {
+        Slot& s = ctx->slots[slot];
+        const uint64_t cnt = std::min(C, n_eval - first);
+        const uint64_t in_bytes = round_up_u64(((cnt + 31) / 32) * (uint64_t)w * 4, 16);
+        SSS_TRY(grow(&s.d_in, &s.in_cap, round_up_u64(C / 32 * (uint64_t)w * 4, 16) + 16));
+        SSS_TRY(grow(&s.d_out, &s.out_cap, C / 8));
+        const uint8_t* src = static_cast<const uint8_t*>(h_packed) + first * (uint64_t)w / 8;
+        SSS_CK(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
+        SSS_TRY(scan_range_impl(ctx, s.d_in, cnt, w, lo, hi, s.d_out, ctx->d_counts, false, s.stream));
+        const uint64_t out_off = first / 8;
+        const uint64_t out_bytes = std::min<uint64_t>(4 * ((cnt + 31) / 32), out_total - out_off);
+        SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_bitvec) + out_off, s.d_out, out_bytes, cudaMemcpyDeviceToHost,
+                               s.stream));
+    }
+    for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
+    if (h_count) SSS_CK(cudaMemcpy(h_count, ctx->d_counts, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return SSS_OK;
+}
+
+static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uint64_t n, int w, const uint32_t* h_lo,
+                            const uint32_t* h_hi, int K, int tail_granule, void* h_out, uint64_t stride_bytes,
+                            uint64_t* h_counts)
+{
+    if (ctx == nullptr || h_packed == nullptr || h_out == nullptr || h_lo == nullptr || h_hi == nullptr)
+        return SSS_ERR_INVALID_ARG;
+    if (w < 1 || w > 32) return SSS_ERR_INVALID_ARG;
+    SSS_TRY(check_k(K));
+    if (tail_granule != 1 && tail_granule != 8 && tail_granule != 32) return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    const uint64_t n_eval = eval_codes_for(n, tail_granule);
+    const uint64_t out_total = out_bytes_for(n, tail_granule);  // per predicate (bitvectors) / rows (linear)
+    if (!linear && stride_bytes < out_total) return SSS_ERR_INVALID_ARG;
+    const uint64_t C = chunk_codes(w / 8.0, K / 8.0);
+    cudaStream_t s0 = ctx->slots[0].stream;
+    SSS_CK(cudaMemcpyAsync(ctx->d_lo, h_lo, (size_t)K * 4, cudaMemcpyHostToDevice, s0));
+    SSS_CK(cudaMemcpyAsync(ctx->d_hi, h_hi, (size_t)K * 4, cudaMemcpyHostToDevice, s0));
+    SSS_CK(cudaMemsetAsync(ctx->d_counts, 0, (size_t)K * sizeof(unsigned long long), s0));
+    SSS_CK(cudaStreamSynchronize(s0));
+    int slot = 0;
+    for (uint64_t first = 0; first < n_eval; first += C, slot = (slot + 1) % kSlots) {
+        Slot& s = ctx->slots[slot];
+        const uint64_t cnt = std::min(C, n_eval - first);
+        const uint64_t in_bytes = round_up_u64(((cnt + 31) / 32) * (uint64_t)w * 4, 16);
+        SSS_TRY(grow(&s.d_in, &s.in_cap, round_up_u64(C / 32 * (uint64_t)w * 4, 16) + 16));
+        SSS_TRY(grow(&s.d_out, &s.out_cap, C / 8 * (uint64_t)K));
+        const uint8_t* src = static_cast<const uint8_t*>(h_packed) + first * (uint64_t)w / 8;
+        SSS_CK(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
+        const uint64_t chunk_stride = C / 8;  // device-side bitvector stride inside the slot
+        SSS_TRY(shared_impl(ctx, linear, s.d_in, cnt, w, ctx->d_lo, ctx->d_hi, K, s.d_out, chunk_stride, ctx->d_counts,
+                            false, s.stream));
+        const uint64_t out_off = first / 8;  // bytes per predicate / rows already produced
+        const uint64_t piece = std::min<uint64_t>(4 * ((cnt + 31) / 32), out_total - out_off);
+        if (linear) {
+            SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_out) + out_off * (uint64_t)K, s.d_out, piece * (uint64_t)K,
+                                   cudaMemcpyDeviceToHost, s.stream));
+        } else {
+            SSS_CK(cudaMemcpy2DAsync(static_cast<uint8_t*>(h_out) + out_off, stride_bytes, s.d_out, chunk_stride, piece,
+                                     (size_t)K, cudaMemcpyDeviceToHost, s.stream));
+        }
+    }
+    for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
+    if (h_counts) SSS_CK(cudaMemcpy(h_counts, ctx->d_counts, (size_t)K * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return SSS_OK;
+}
+
+int sss_host_shared_scan(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, const uint32_t* h_lo,
+                         const uint32_t* h_hi, int K, int tail_granule, void* h_bitvecs, uint64_t stride_bytes,
+                         uint64_t* h_counts)
+{
+    return host_shared_impl(ctx, false, h_packed, n, w, h_lo, h_hi, K, tail_granule, h_bitvecs, stride_bytes, h_counts);
+}
+
+int sss_host_shared_scan_linear(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, const uint32_t* h_lo,
+                                const uint32_t* h_hi, int K, int tail_granule, void* h_out, uint64_t* h_counts)
+{
+    return host_shared_impl(ctx, true, h_packed, n, w, h_lo, h_hi, K, tail_granule, h_out, 0, h_counts);
+}
+
+int sss_host_pack(sss_ctx* ctx, const uint32_t* h_codes, uint64_t n, int w, void* h_packed)
+{
+    if (ctx == nullptr || h_packed == nullptr || (h_codes == nullptr && n != 0) || w < 1 || w > 32)
+        return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    const size_t total = sss_packed_bytes(n, w);
+    std::memset(h_packed, 0, total);  // padding (and everything, for n == 0)
+    const uint64_t C = chunk_codes(4.0, w / 8.0);
+    int slot = 0;
+    for (uint64_t first = 0; first < n; first += C, slot = (slot + 1) % kSlots) {
+        Slot& s = ctx->slots[slot];
+        const uint64_t cnt = std::min(C, n - first);
+        const uint64_t words = (cnt * (uint64_t)w + 31) / 32;
+        SSS_TRY(grow(&s.d_in, &s.in_cap, C * 4));
+        SSS_TRY(grow(&s.d_out, &s.out_cap, C / 32 * (uint64_t)w * 4 + 16));
+        SSS_CK(cudaMemcpyAsync(s.d_in, h_codes + first, cnt * 4, cudaMemcpyHostToDevice, s.stream));
+        SSS_CK(launch_pack(ctx->dev, static_cast<const uint32_t*>(s.d_in), cnt, w, static_cast<uint32_t*>(s.d_out), words,
+                           s.stream));
+        const uint64_t off = first * (uint64_t)w / 8;
+        const uint64_t bytes = std::min<uint64_t>(words * 4, total - off);
+        SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_packed) + off, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
+    return SSS_OK;
+}
+
+void* sss_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void sss_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int sss_host_register(void* p, size_t bytes) { return cuda_status(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); }
+int sss_host_unregister(void* p) { return cuda_status(cudaHostUnregister(p)); }
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// common.cuh -- device-side building blocks shared by every kernel family (sm_100a only).
+//
+//   * mbarrier + cp.async.bulk (TMA 1-D bulk copy) wrappers,
+//   * TileRing: a multi-stage shared-memory ring fed by one elected thread with bulk copies of
+//     contiguous packed-column tiles (persistent CTAs, static round-robin tile order),
+//   * warp/CTA reduction of match counts into a 64-bit global counter.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/simd_scan_commons.hpp"
+
+#if !defined(__CUDA_ARCH__) || (__CUDA_ARCH__ >= 1000)
+#else
+#error "shared_simd_scan_b200 kernels are written for sm_100a only"
+#endif
+
+namespace sss {
+
+constexpr int kThreads = 256;  // every streaming kernel uses 256-thread CTAs
+constexpr int kWarps = kThreads / 32;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+
+// make mbarrier.init visible to the async (TMA) proxy before the first bulk copy targets it
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// order prior generic-proxy smem reads/writes before subsequent async-proxy (bulk copy) writes
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// L2 eviction policy for data that is read exactly once (the packed column)
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// streaming stores: results are written once and never re-read by these kernels
+__device__ __forceinline__ void st_stream_u32(uint32_t* p, uint32_t v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream_v4(int4* p, int4 v) { __stcs(p, v); }
+
+// ---- tile ring --------------------------------------------------------------------------------
+//
+// The packed column is cut into tiles of kTileBytes contiguous bytes (a whole number of 32-code
+// blocks, so every tile starts 16-byte aligned for any w).  CTA b owns tiles b, b+grid, b+2*grid...
+// Thread 0 keeps kStages bulk copies in flight; all threads wait on the stage's "full" mbarrier,
+// consume the tile from shared memory, meet at __syncthreads, and thread 0 refills the stage.
+//
+// Shared memory layout: [kStages][kTileBytes + kPadBytes] then kStages mbarriers.
+template <int kTileBytes, int kStages, int kPadBytes = 16>
+struct TileRing {
+    static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+    static constexpr int kStageBytes = kTileBytes + kPadBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStages * 8;
+    static_assert(kStageBytes % 16 == 0, "stage base must stay 16-byte aligned");
+
+    uint8_t* base;
+    uint64_t* full;
+    const uint8_t* src;
+    uint64_t src_bytes;   // readable bytes of the packed column, rounded up to 16
+    uint64_t num_tiles;
+    uint64_t policy;
+
+    __device__ __forceinline__ TileRing(uint8_t* smem, const void* packed, uint64_t readable_bytes16)
+        : base(smem), full(reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes)),
+          src(static_cast<const uint8_t*>(packed)), src_bytes(readable_bytes16),
+          num_tiles((readable_bytes16 + kTileBytes - 1) / kTileBytes), policy(0)
+    {
+    }
+
+    __device__ __forceinline__ const uint32_t* stage_words(int stage) const
+    {
+        return reinterpret_cast<const uint32_t*>(base + stage * kStageBytes);
+    }
+
+    // thread 0 only
+    __device__ __forceinline__ void issue(uint64_t tile, int stage)
+    {
+        const uint64_t off = tile * (uint64_t)kTileBytes;
+        const uint64_t left = src_bytes - off;
+        const uint32_t bytes = left < (uint64_t)kTileBytes ? (uint32_t)left : (uint32_t)kTileBytes;
+        mbar_arrive_expect_tx(&full[stage], bytes);
+        bulk_g2s(base + stage * kStageBytes, src + off, bytes, &full[stage], policy);
+    }
+
+    // all threads; returns after the barriers are initialised and the first kStages copies are issued
+    __device__ __forceinline__ void start()
+    {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
+            fence_mbar_init();
+            policy = l2_policy_evict_first();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t t = blockIdx.x;
+            for (int s = 0; s < kStages && t < num_tiles; s++, t += gridDim.x) issue(t, s);
+        }
+    }
+
+    __device__ __forceinline__ void wait(uint32_t iter)
+    {
+        mbar_wait(&full[iter % kStages], (iter / kStages) & 1u);
+    }
+
+    // all threads, after the tile of iteration `iter` has been consumed
+    __device__ __forceinline__ void release(uint32_t iter, uint64_t tile)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint64_t next = tile + (uint64_t)kStages * gridDim.x;
+            if (next < num_tiles) {
+                fence_proxy_async();
+                issue(next, iter % kStages);
+            }
+        }
+    }
+};
+
+// ---- code extraction --------------------------------------------------------------------------
+//
+// Code J of a 32-code block (W consecutive words in registers) moved to the TOP W bits of a 32-bit
+// value.  Word index and shift distance are compile-time constants (sss::code_slot); the low 32-W
+// bits hold leftovers of the preceding codes or zeros, which the aligned range compare ignores.
+// Counterpart of the reference's pshufb byte gather + per-lane shift masks (commons :5-50).
+template <int W, int J>
+__device__ __forceinline__ uint32_t left_aligned_code(const uint32_t (&x)[W])
+{
+    constexpr CodeSlot s = code_slot(W, J);
+    if constexpr (s.end_shift == 32) {
+        return x[s.last_word];
+    } else if constexpr (!s.straddles) {
+        return x[s.last_word] << (32 - s.end_shift);
+    } else {
+        return __funnelshift_r(x[s.first_word], x[s.last_word], s.end_shift);
+    }
+}
+
+template <int W, int J>
+struct LeftAlignAll {
+    static __device__ __forceinline__ void run(const uint32_t (&x)[W], uint32_t (&t)[32])
+    {
+        t[J] = left_aligned_code<W, J>(x);
+        LeftAlignAll<W, J + 1>::run(x, t);
+    }
+};
+template <int W>
+struct LeftAlignAll<W, 32> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[W], uint32_t (&)[32]) {}
+};
+
+// ---- count reduction --------------------------------------------------------------------------
+
+// Sum `v` over the CTA and add it to *global (one 64-bit atomic per CTA).  All threads call.
+__device__ __forceinline__ void cta_add_u64(uint32_t v, unsigned long long* global)
+{
+    __shared__ uint32_t warp_sums[kWarps];
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+#pragma unroll
+        for (int i = 0; i < kWarps; i++) s += warp_sums[i];
+        if (s) atomicAdd(global, s);
+    }
+}
+
+}  // namespace sss

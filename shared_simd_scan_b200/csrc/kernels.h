@@ -1,0 +1,49 @@
+// kernels.h -- internal launch interface between the C-ABI shim (capi.cu) and the kernel families.
+// Every launcher dispatches the runtime width to a template<int W> kernel through a 32-entry table
+// (the reference fixes the width at compile time: `#define BITS_NEEDED 9`, src/simd_scan.hpp:12).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/simd_scan_commons.hpp"
+
+namespace sss {
+
+struct Device {
+    int ordinal;
+    int sm_count;
+    int smem_optin;  // max dynamic shared memory per CTA
+};
+
+// scan.cu -- fused unpack + range compare -> bitvector (+count)
+cudaError_t launch_scan_range(const Device& dev, const void* packed, uint64_t n, int w, AlignedRange r,
+                              uint32_t* bitvec, unsigned long long* count, cudaStream_t stream);
+
+// unpack.cu -- packed -> int32 per code
+cudaError_t launch_unpack(const Device& dev, const void* packed, uint64_t n, int w, int32_t* out,
+                          cudaStream_t stream);
+
+// shared.cu -- K predicates in one pass -> K bitvectors (+K counts)
+cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n, int w, const uint32_t* lo,
+                               const uint32_t* hi, int K, uint32_t* bitvecs, uint64_t stride_words,
+                               unsigned long long* counts, cudaStream_t stream);
+
+// linear.cu -- K predicates in one pass -> [ceil(n/8)][K] byte matrix (+K counts)
+cudaError_t launch_shared_scan_linear(const Device& dev, const void* packed, uint64_t n, int w,
+                                      const uint32_t* lo, const uint32_t* hi, int K, uint8_t* out,
+                                      unsigned long long* counts, cudaStream_t stream);
+
+// pack.cu -- compressor and synthetic-column generator
+cudaError_t launch_pack(const Device& dev, const uint32_t* codes, uint64_t n, int w, uint32_t* packed,
+                        uint64_t packed_words, cudaStream_t stream);
+cudaError_t launch_generate_packed(const Device& dev, uint32_t* packed, uint64_t packed_words, uint64_t n, int w,
+                                   uint64_t seed, uint64_t first_index, cudaStream_t stream);
+
+// positions.cu -- bitvector -> ascending position list
+size_t positions_workspace_bytes(uint64_t n);
+cudaError_t launch_positions(const Device& dev, const uint32_t* bitvec, uint64_t n, uint64_t base,
+                             unsigned long long* positions, uint64_t capacity, unsigned long long* num,
+                             void* workspace, cudaStream_t stream);
+
+}  // namespace sss

@@ -1,0 +1,230 @@
+"""GPU parity: the CUDA path, called through the C ABI, must be bit-exact with the CPU oracle
+(and with the committed goldens of the unmodified reference) on the same seeded inputs.
+
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import binding as B  # noqa: E402  (the checker, never the thing measured)
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_w*.npz")))
+ALL_W = list(range(1, 33))
+
+
+@pytest.fixture(scope="module")
+def sss():
+    import shared_simd_scan_b200 as m
+    from shared_simd_scan_b200 import api
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    m.Context.current()  # fails loudly if libsss_b200.so is missing or the device is unsuitable
+    return api
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def column(n, w, seed):
+    codes = B.generate_codes(n, w, seed=seed)
+    return codes, B.pack(codes, w)
+
+
+SIZES = [1, 31, 32, 33, 1000, 8192, 8192 * 3 + 5, 300_007]
+
+
+@pytest.mark.parametrize("w", ALL_W)
+def test_unpack_matches_oracle(sss, w):
+    for n in SIZES:
+        codes, packed = column(n, w, seed=100 + w)
+        out = host(sss.decompress(dev(packed), n, w))
+        assert (out == B.unpack(packed, n, w)).all(), (w, n)
+        assert (out.astype(np.uint32) == codes).all()
+
+
+@pytest.mark.parametrize("w", ALL_W)
+def test_scan_matches_oracle(sss, w):
+    m = (1 << w) - 1
+    for n in SIZES:
+        codes, packed = column(n, w, seed=200 + w)
+        d_packed = dev(packed)
+        ranges = [(int(codes[n // 2]), int(codes[n // 2])), (0, 0), (m, m), (m // 4, m // 2 + 1), (0, m), (5, 4)]
+        for lo, hi in ranges:
+            bv, cnt = sss.scan(d_packed, n, w, lo, hi)
+            exp, ecnt = B.scan_range(packed, n, w, lo, hi, granule=1)
+            got = host(bv)[: 4 * ((n + 31) // 32)]
+            assert (got[: len(exp)] == exp).all(), (w, n, lo, hi)
+            assert not got[len(exp):].any(), "bits >= n must be zero"
+            assert int(cnt.item()) == ecnt, (w, n, lo, hi)
+
+
+@pytest.mark.parametrize("w", ALL_W)
+def test_pack_matches_oracle(sss, w):
+    for n in [1, 33, 1000, 70_001]:
+        codes = B.generate_codes(n, w, seed=300 + w)
+        exp = B.pack(codes, w)
+        got = host(sss.compress(dev(codes.view(np.int32)), w))
+        assert (got == exp).all(), (w, n)
+        # device generator == host generator, packed
+        gen = host(sss.generate_packed(n, w, seed=300 + w))
+        assert (gen == exp).all(), (w, n)
+        # first_index offsets the counter stream
+        gen2 = host(sss.generate_packed(n - n // 2, w, seed=300 + w, first_index=n // 2))
+        assert (B.unpack(gen2, n - n // 2, w).astype(np.uint32) == codes[n // 2:]).all()
+
+
+@pytest.mark.parametrize("w", [1, 5, 9, 16, 17, 23, 31, 32])
+@pytest.mark.parametrize("K", [1, 3, 4, 8, 64])
+def test_shared_scan_matches_oracle(sss, w, K):
+    m = (1 << w) - 1
+    rng = np.random.default_rng(w * 1000 + K)
+    for n in [31, 1000, 8192 * 2 + 77]:
+        codes, packed = column(n, w, seed=400 + w)
+        lo = rng.integers(0, m + 1, size=K, dtype=np.uint64)
+        span = rng.integers(0, max(1, (m + 1) // max(K // 2, 1)) + 1, size=K, dtype=np.uint64)
+        hi = np.minimum(lo + span, m)
+        lo[0] = hi[0] = int(codes[0])          # an equality predicate that certainly hits
+        if K > 2:
+            lo[2], hi[2] = 7, 3                # an empty range
+        exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
+        bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi)
+        got = host(bv)
+        nb = (n + 7) // 8
+        assert (got[:, :nb] == exp).all(), (w, K, n)
+        assert not got[:, nb: 4 * ((n + 31) // 32)].any()
+        assert (host(cnt).astype(np.uint64) == ecnt).all()
+
+        lexp, lcnt = B.shared_scan_linear(packed, n, w, lo, hi, granule=1)
+        lin, cnt2 = sss.shared_scan_linear(dev(packed), n, w, lo, hi)
+        lgot = host(lin)
+        assert (lgot[:nb] == lexp).all(), (w, K, n)
+        assert not lgot[nb:].any()
+        assert (host(cnt2).astype(np.uint64) == lcnt).all()
+
+
+def test_shared_scan_k1024_duplicates(sss):
+    # config 4 shape (w = 9, K = 1024 => duplicate keys), small n
+    w, n, K = 9, 5003, 1024
+    codes, packed = column(n, w, seed=9)
+    keys = np.array([(i * 7) % 512 for i in range(K)], dtype=np.uint32)
+    lexp, lcnt = B.shared_scan_linear(packed, n, w, keys, keys, granule=1)
+    lin, cnt = sss.shared_scan_linear(dev(packed), n, w, keys, keys)
+    assert (host(lin)[: (n + 7) // 8] == lexp).all()
+    assert (host(cnt).astype(np.uint64) == lcnt).all()
+    exp, ecnt = B.shared_scan(packed, n, w, keys, keys, granule=1)
+    bv, cnt = sss.shared_scan(dev(packed), n, w, keys, keys)
+    assert (host(bv)[:, : (n + 7) // 8] == exp).all()
+    assert (host(cnt).astype(np.uint64) == ecnt).all()
+
+
+@pytest.mark.parametrize("w", [3, 11, 32])
+def test_positions(sss, w):
+    for n in [1, 77, 40_000, 1_000_003]:
+        codes, packed = column(n, w, seed=500 + w)
+        m = (1 << w) - 1
+        for lo, hi in [(0, m // 3), (int(codes[0]), int(codes[0])), (1, 0)]:
+            bv, cnt = sss.scan(dev(packed), n, w, lo, hi)
+            pos, num = sss.positions(bv, n, base=1 << 35)
+            exp = B.positions(host(bv), n, base=1 << 35)
+            k = int(num.item())
+            assert k == len(exp) == int(cnt.item())
+            assert (host(pos)[:k].astype(np.uint64) == exp).all()
+        # capacity smaller than the number of matches: first `capacity` positions, full count
+        bv, cnt = sss.scan(dev(packed), n, w, 0, m)
+        pos, num = sss.positions(bv, n, capacity=min(n, 10))
+        assert int(num.item()) == n and (host(pos)[: min(n, 10)] == np.arange(min(n, 10))).all()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_host_api_reproduces_reference_goldens(sss, path):
+    """The host-buffer C-ABI calls (what include/simd_scan.hpp wraps) against vectors produced by the
+    unmodified reference, including each variant's tail granule."""
+    g = np.load(path)
+    w, n = int(g["w"]), int(g["n"])
+    packed = np.ascontiguousarray(g["packed"])
+    u32 = lambda k: int(k) & 0xFFFFFFFF  # noqa: E731
+    assert (sss.host_decompress(packed, n, w).astype(np.uint32) == g["codes"]).all()
+    if g["packed_by"] == "reference":
+        assert (sss.host_compress(g["codes"], w)[: len(packed)] == packed[: sss.packed_bytes(n, w)]).all()
+    for i, key in enumerate(g["keys"]):
+        out, hits = sss.host_scan(packed, n, w, u32(key), tail_granule=8)
+        assert (out == g["scan_128"][i]).all() and hits == int(g["hits_128"][i])
+        out, hits = sss.host_scan(packed, n, w, u32(key), tail_granule=32)
+        assert (out == g["scan_128_unrolled"][i]).all() and hits == int(g["hits_128_unrolled"][i])
+    skeys = [u32(k) for k in g["shared_keys"]]
+    outs, _ = sss.host_shared_scan(packed, n, w, skeys, tail_granule=8)
+    assert (outs == g["shared_128_standard"]).all()
+    outs, _ = sss.host_shared_scan(packed, n, w, skeys, tail_granule=32)
+    assert (outs == g["shared_128_standard_unrolled"]).all()
+    lin, _ = sss.host_shared_scan_linear(packed, n, w, skeys, tail_granule=8)
+    assert (lin == g["linear_standard"]).all() and (lin == g["linear_simple"]).all()
+
+
+def test_host_api_chunked_pipeline(sss):
+    """n large enough for several staging chunks (64 MiB each): equals the device-resident path."""
+    w, n = 13, (1 << 26) + 12345
+    d_packed = sss.generate_packed(n, w, seed=77)
+    torch.cuda.synchronize()
+    packed = host(d_packed)
+    lo, hi = 100, 4000
+    bv, cnt = sss.scan(d_packed, n, w, lo, hi)
+    out, hits = sss.host_scan(packed, n, w, lo, hi, tail_granule=1)
+    nb = (n + 7) // 8
+    assert (out[:nb] == host(bv)[:nb]).all() and hits == int(cnt.item())
+    # and a sample of it against the oracle
+    m = 1 << 20
+    exp, _ = B.scan_range(packed, m, w, lo, hi, granule=1)
+    assert (out[: m // 8] == exp).all()
+    dec = sss.host_decompress(packed, n, w)
+    assert (dec == host(sss.decompress(d_packed, n, w))).all()
+
+
+@pytest.mark.parametrize("w", [1, 4, 11, 17, 32])
+def test_full_size_properties(sss, w):
+    """BASELINE sizes (2^30 codes) through size-independent properties: counts add up over a
+    partition of the domain, bitvectors of the parts are disjoint and OR to the whole, count ==
+    popcount, unpack -> pack round trip, and a window of the result equals the oracle."""
+    n = 1 << 30
+    m = (1 << w) - 1
+    d_packed = sss.generate_packed(n, w, seed=42 + w)
+    mid = m // 3
+    bv_a, c_a = sss.scan(d_packed, n, w, 0, mid)
+    bv_b, c_b = sss.scan(d_packed, n, w, mid + 1, m)
+    bv_all, c_all = sss.scan(d_packed, n, w, 0, m)
+    assert int(c_all.item()) == n and int(c_a.item()) + int(c_b.item()) == n
+    nb = n // 8
+    a64, b64 = bv_a[:nb].view(torch.int64), bv_b[:nb].view(torch.int64)
+    assert not (a64 & b64).any() and ((a64 | b64) == -1).all()
+    # popcount(bitvec) == count (per-byte LUT on the device)
+    lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device="cuda")
+    pop = 0
+    for part in bv_a[:nb].split(1 << 27):
+        pop += int(lut[part.long()].sum().item())
+    assert pop == int(c_a.item())
+    # window vs oracle
+    win = 1 << 16
+    first = (n // 2 // 1024) * 1024
+    byte0 = first * w // 8
+    host_packed = np.zeros(B.compressed_buffer_size(w, win), dtype=np.uint8)
+    chunk = host(d_packed[byte0: byte0 + (win * w + 7) // 8])
+    host_packed[: len(chunk)] = chunk
+    exp, _ = B.scan_range(host_packed, win, w, 0, mid, granule=1)
+    assert (host(bv_a[first // 8: first // 8 + win // 8]) == exp).all()
+    del bv_a, bv_b, bv_all
+    # unpack -> pack round trip on 2^28 codes
+    n2 = 1 << 28
+    dec = sss.decompress(d_packed, n2, w)
+    re = sss.compress(dec, w)
+    payload = n2 * w // 8
+    assert torch.equal(re[:payload], d_packed[:payload])
