@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract for shared_simd_scan_b200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload ("step"): one pass of the hot path over one batch of synthetic input =
+the fused unpack + range-predicate scan (bitvector + match count out) over a uniform-random column
+of 2^30 codes at EVERY bit width 1..32 -- the configuration BASELINE.json's target is quoted on
+("single-GPU, 1B codes, fused unpack+scan at every bit width 1-32").  32 kernel launches per step.
+With N GPUs every rank scans its own range shard of a column of N * 2^30 codes per width (weak
+scaling), and the per-width match counts are combined with one small NCCL allreduce per step.
+
+value   = codes scanned by all ranks / max-over-ranks device time (CUDA events, inputs resident in HBM)
+e2e     = the same sweep through the host-buffer C-ABI call the C++ drop-in layer uses
+          (sss_host_scan_range: pinned host buffers, H2D + kernel + D2H inside the timed region)
+roofline= algorithmic bytes (w/8 + 1/8 per code) / measured kernel time vs. MEASURED_PEAKS.json hbm_gbs
+cpu_baseline / --impl reference = the reference's own AVX2 scan (oracle/_ref) on the host cores.
+Extra keys (per_width, shared, unpack) carry the per-bit-width and per-K numbers the metric asks for.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTHS = list(range(1, 33))
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def predicate(w):
+    """Range predicate of the sweep: [m/4, m/2] (about 25 % selectivity for w >= 3)."""
+    m = (1 << w) - 1
+    return m // 4, m // 2
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l for (t, l) in self.lines if (t0 is None or t >= t0 - 0.05) and (t1 is None or t <= t1 + 0.15)]
+        if not rows:
+            rows = [l for (_, l) in self.lines]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            p = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, p[2:]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the ONLY places that execute anything under oracle/)
+# ---------------------------------------------------------------------------------------------
+
+def cpu_reference_sweep(logn, reps, threads):
+    """The reference's own CPU scan over a bounded sample: 2^logn uniform codes per width.
+
+    oracle/_ref (the unmodified reference compiled per width) when present: scan_256_unrolled for
+    w <= 16 (the "reference AVX2 scan"), scan_128_unrolled above (the AVX path is only exact up to
+    16 bits); every host thread scans its own range of the column.  If
+    oracle/_ref is absent the plain-C oracle port is timed instead (kind "port").
+    Returns (codes_per_s over the whole sweep, per-width seconds, kind)."""
+    import numpy as np
+    from oracle import binding as B
+    n = 1 << logn
+    rng = np.random.default_rng(42)
+    per_w = {}
+    kind = "reference" if all(B.ref_available(w) for w in WIDTHS) else "port"
+    for w in WIDTHS:
+        nbytes = B.compressed_buffer_size(w, n)
+        packed = np.zeros(nbytes, dtype=np.uint8)
+        payload = n * w // 8
+        packed[:payload] = np.frombuffer(rng.bytes(payload), dtype=np.uint8)  # uniform bits == uniform codes
+        key = 3 & ((1 << w) - 1)  # the reference only has equality predicates (src/simd_scan.cpp:47)
+        if kind == "reference":
+            variant = B.SCAN["256_unrolled"] if w <= 16 else B.SCAN["128_unrolled"]
+            import ctypes as C
+            hits = C.c_longlong(0)
+            s = B.ref(w).ref_time_scan(variant, key, packed.ctypes.data, n, threads, reps, C.byref(hits))
+        else:
+            s, _ = B.time_scan_range(packed, n, w, key, key, threads, reps)
+        per_w[w] = s
+    total = sum(per_w.values())
+    return len(WIDTHS) * n / total, per_w, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    logn = args.ref_logn
+    # warm-up + timed steps: each step = the sweep over the bounded sample
+    for _ in range(args.warmup):
+        cpu_reference_sweep(min(logn, 22), 1, threads)
+    t_steps = []
+    kind = "port"
+    for _ in range(args.steps):
+        v, per_w, kind = cpu_reference_sweep(logn, 1, threads)
+        t_steps.append(sum(per_w.values()))
+    sec = statistics.mean(t_steps)
+    value = len(WIDTHS) * (1 << logn) / sec
+    sample = (f"bounded sample: 2^{logn} uniform codes per width (workload: 2^{args.logn}), equality key 3; "
+              f"{'scan_256_unrolled (w<=16) / scan_128_unrolled (w>16) of the unmodified reference' if kind == 'reference' else 'plain-C oracle port'}"
+              f", column range-partitioned over {threads} host threads")
+    line = {
+        "impl": "reference", "metric": "scanned_codes_per_s", "value": value, "unit": "codes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "codes/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "codes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args):
+    return {"workload": f"fused unpack+range-scan sweep, bit widths 1-32, 2^{args.logn} uniform-random codes per "
+                        "width per GPU, range predicate [m/4, m/2], bitvector + match count out",
+            "codes_per_width_per_gpu": 1 << args.logn, "widths": "1-32", "predicate": "lo=m/4, hi=m/2 (m=2^w-1)",
+            "l2": "inputs larger than L2; every step streams ~70 GB through 32 different columns",
+            "parallelism": f"range-sharded column, {args.gpus} GPU(s), NCCL allreduce of match counts"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from shared_simd_scan_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: shared_simd_scan_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = 1 << args.logn
+    peak, peak_src = measured_peak()
+
+    # ---- resident inputs: one packed column per width, this rank's shard of the global column ----
+    columns = {w: api.generate_packed(n, w, seed=42 + w, first_index=rank * n) for w in WIDTHS}
+    bitvec = torch.empty(api.bitvec_bytes(n), dtype=torch.uint8, device="cuda")
+    counts = torch.zeros(len(WIDTHS), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+
+    def step(events=None):
+        for i, w in enumerate(WIDTHS):
+            if events is not None:
+                events[i].record()
+            lo, hi = predicate(w)
+            api.scan(columns[w], n, w, lo, hi, out=bitvec, count=counts[i:i + 1])
+        if events is not None:
+            events[len(WIDTHS)].record()
+        if world > 1:
+            dist.all_reduce(counts)  # the only collective on the path: 32 x int64
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(WIDTHS) + 1)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.perf_counter()
+    t_begin.record()
+    for k in range(args.steps):
+        step(ev[k])
+    t_end.record()
+    barrier()
+    wall1 = time.perf_counter()
+    clocks = sampler.stop(wall0, wall1)
+    dev_ms = t_begin.elapsed_time(t_end)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = world * len(WIDTHS) * n / (ms_per_step * 1e-3)
+
+    # per-width kernel time (events bracket each launch on the launching stream)
+    per_width = []
+    total_kernel_ms, total_bytes = 0.0, 0.0
+    for i, w in enumerate(WIDTHS):
+        ms = statistics.mean(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps))
+        b = n * (w / 8 + 1 / 8)
+        total_kernel_ms += ms
+        total_bytes += b
+        per_width.append({"w": w, "ms": round(ms, 4), "gcodes_per_s": round(n / ms / 1e6, 1),
+                          "gb_per_s": round(b / ms / 1e6, 1), "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4),
+                          "frac_of_8TBps": round(b / ms / 1e6 / 8000.0, 4)})
+    achieved = total_bytes / (total_kernel_ms * 1e-3) / 1e9
+    final_counts = counts.cpu().tolist()
+
+    # ---- e2e: the host-buffer C-ABI call (what include/simd_scan.hpp wraps), pinned host memory ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    max_bytes = api.packed_bytes(n, 32)
+    h_in = api.pinned_empty(max_bytes)
+    h_out = api.pinned_empty(api.bitvec_bytes(n))
+    e2e_sec, h2d, d2h = [], 0, 0
+    e2e_counts = []
+    for s in range(e2e_steps + 1):  # first pass = warm-up (staging buffers get allocated)
+        sec = 0.0
+        h2d = d2h = 0
+        for w in WIDTHS:
+            nb = api.packed_bytes(n, w)
+            h_in[:nb].copy_(columns[w][:nb])  # refill the host column (untimed)
+            torch.cuda.synchronize()
+            lo, hi = predicate(w)
+            t0 = time.perf_counter()
+            _, c = api.host_scan(h_in, n, w, lo, hi, tail_granule=1, out=h_out)
+            sec += time.perf_counter() - t0
+            h2d += (n // 32) * w * 4
+            d2h += n // 8 + 8
+            if s == e2e_steps:
+                e2e_counts.append(c)
+        if s > 0:
+            e2e_sec.append(sec)
+    te = torch.tensor([statistics.mean(e2e_sec)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * len(WIDTHS) * n / float(te.item())
+    del h_in, h_out
+    if world == 1:
+        assert e2e_counts == final_counts, "host-buffer path and device-resident path disagree on the match counts"
+
+    line = {
+        "metric": "scanned_codes_per_s", "value": value, "unit": "codes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "codes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "sss_host_scan_range (pinned host buffers, 64 MiB chunks, 3 streams)"},
+        "gpu_launches": args.steps * len(WIDTHS),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "kernel": "sss::scan_range_kernel<W>, aggregated over the 32 launches of a step "
+                               "(bytes = n*(w/8+1/8) per launch; per-launch numbers in per_width)",
+                     "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},
+        "per_width": per_width,
+    }
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        line.update(extras(args, api, columns, n, peak))
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        v, per_w, kind = cpu_reference_sweep(args.cpu_logn, 2, threads)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "codes/s", "cores": threads, "kind": kind,
+            "sample": f"same sweep on 2^{args.cpu_logn} uniform codes per width (best of 2), equality key 3; "
+                      "scan_256_unrolled (w<=16) / scan_128_unrolled (w>16) of the unmodified reference, column "
+                      f"range-partitioned over {threads} host threads; {time.perf_counter() - t0:.1f} s of wall time"}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def extras(args, api, columns, n, peak):
+    """Per-K shared-scan numbers and the decompression sweep (BASELINE.json configs 2-4), measured
+    after the timed steps with the same event discipline (3 warm-ups, mean of 5)."""
+    import torch
+
+    def timed(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+
+    out = {"shared": [], "unpack": []}
+    g = torch.Generator().manual_seed(42)
+    for kind, w, K, logn in (("shared", 17, 8, 30), ("shared", 17, 64, 30), ("shared", 23, 64, 30),
+                             ("linear", 9, 64, 30), ("linear", 9, 1024, 27)):
+        nn = 1 << min(logn, args.logn)
+        m = (1 << w) - 1
+        lo = torch.randint(0, m + 1, (K,), generator=g)
+        hi = torch.clamp(lo + torch.randint(0, max(2, 2 * (m + 1) // K), (K,), generator=g), max=m)
+        lo_d, hi_d = lo.to(torch.int32).cuda(), hi.to(torch.int32).cuda()
+        cnt = torch.empty(K, dtype=torch.int64, device="cuda")
+        if kind == "shared":
+            buf = torch.empty((K, (api.bitvec_bytes(nn) + 15) // 16 * 16), dtype=torch.uint8, device="cuda")
+            ms = timed(lambda: api.shared_scan(columns[w], nn, w, lo_d, hi_d, out=buf, counts=cnt))
+        else:
+            buf = torch.empty((4 * ((nn + 31) // 32), K), dtype=torch.uint8, device="cuda")
+            ms = timed(lambda: api.shared_scan_linear(columns[w], nn, w, lo_d, hi_d, out=buf, counts=cnt))
+        b = nn * (w / 8 + K / 8)
+        out["shared"].append({"op": kind, "w": w, "K": K, "n": nn, "ms": round(ms, 3),
+                              "gcodes_per_s": round(nn / ms / 1e6, 2), "gb_per_s": round(b / ms / 1e6, 1),
+                              "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4)})
+        del buf
+    n2 = 1 << min(28, args.logn)
+    dec = torch.empty(n2, dtype=torch.int32, device="cuda")
+    for w in WIDTHS:
+        ms = timed(lambda: api.decompress(columns[w], n2, w, out=dec), reps=3, warm=2)
+        b = n2 * (w / 8 + 4)
+        out["unpack"].append({"w": w, "n": n2, "ms": round(ms, 4), "gcodes_per_s": round(n2 / ms / 1e6, 1),
+                              "gb_per_s": round(b / ms / 1e6, 1), "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4)})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--logn", type=int, default=30, help="log2 codes per width per GPU (BASELINE: 30)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-logn", type=int, default=27, help="cpu_baseline sample: log2 codes per width")
+    ap.add_argument("--ref-logn", type=int, default=26, help="--impl reference sample: log2 codes per width per step")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -41,6 +41,14 @@ extern "C" {
 #define SSS_ERR_NO_DEVICE (-3)
 #define SSS_ERR_CUDA_BASE 1000 /* 1000 + cudaError_t */
 
+/* tail_granule values of the host entry points: how far past code n-1 the reference variant being
+ * replaced keeps evaluating the predicate on the buffer padding. */
+#define SSS_TAIL_EXACT 1       /* canonical: nothing past n */
+#define SSS_TAIL_8 8           /* scan_128 / scan_256 / shared_*_standard / linear_*: next multiple of 8 */
+#define SSS_TAIL_32 32         /* *_unrolled: next multiple of 32, whole 32-bit words written */
+#define SSS_TAIL_CURSOR32 132  /* shared_scan_*_parallel: every code that starts inside ceil(w*n/32) words */
+#define SSS_TAIL_CURSOR64 164  /* scan_unvectorized: every code that starts inside ceil(w*n/64) 64-bit words */
+
 #define SSS_MAX_PREDICATES 1024 /* largest K of the reference's shared scans (src/simd_scan_shared_linear.cpp:76) */
 
 typedef struct sss_ctx sss_ctx;
@@ -56,6 +64,11 @@ int sss_ctx_sm_count(const sss_ctx* ctx);
 size_t sss_packed_bytes(uint64_t n, int w);  /* compressed_buffer_size, src/simd_scan.hpp:20-26 */
 size_t sss_unpack_bytes(uint64_t n);         /* decompression_output_buffer_size, :28-33 */
 size_t sss_bitvec_bytes(uint64_t n);         /* scan_output_buffer_size, :35-40 */
+
+/* Pure arithmetic (no device needed): number of codes a tail mode evaluates and the number of
+ * output bytes (per bitvector, or rows for the linear layout) it writes.  0 for a bad mode. */
+uint64_t sss_tail_eval_codes(uint64_t n, int w, int tail_granule);
+uint64_t sss_tail_out_bytes(uint64_t n, int w, int tail_granule);
 
 /* ---- device-resident entry points (pointers are device pointers) --------------------------- */
 
@@ -97,10 +110,10 @@ int sss_shared_scan_linear(sss_ctx* ctx, const void* d_packed, uint64_t n, int w
 
 /* ---- host-buffer entry points (what the C++ drop-in layer calls) --------------------------------
  * Synchronous: packed input is copied host->device in chunks overlapped with the kernels and the
- * device->host copies of the results.  tail_granule in {1, 8, 32} reproduces the tail behaviour of
- * the reference variant being replaced: codes in [n, round_up(n, granule))
- * are decoded from the buffer padding and evaluated, exactly like the reference's SIMD loops;
- * ceil(n/8) bytes (granule 1, 8) or 4*ceil(n/32) bytes (granule 32) are written, nothing beyond.
+ * device->host copies of the results.  tail_granule (SSS_TAIL_*) reproduces the tail behaviour of
+ * the reference variant being replaced: codes in
+ * [n, sss_tail_eval_codes(n, w, mode)) are decoded from the buffer padding and evaluated, exactly
+ * like the reference's loops; sss_tail_out_bytes(n, w, mode) bytes are written, nothing beyond.
  * Pinned buffers (sss_host_alloc / sss_host_register) transfer at full PCIe speed. */
 int sss_host_unpack(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, int32_t* h_out);
 int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, uint32_t lo,
@@ -108,6 +121,11 @@ int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, u
 int sss_host_shared_scan(sss_ctx* ctx, const void* h_packed, uint64_t n, int w,
                          const uint32_t* h_lo, const uint32_t* h_hi, int K, int tail_granule,
                          void* h_bitvecs, uint64_t stride_bytes, uint64_t* h_counts);
+/* same, one separately allocated bitvector per predicate (std::vector<std::vector<uint8_t>>& outputs of
+ * the reference, src/simd_scan.hpp:102-113) */
+int sss_host_shared_scan_ptrs(sss_ctx* ctx, const void* h_packed, uint64_t n, int w,
+                              const uint32_t* h_lo, const uint32_t* h_hi, int K, int tail_granule,
+                              void* const* h_bitvec_ptrs, uint64_t* h_counts);
 int sss_host_shared_scan_linear(sss_ctx* ctx, const void* h_packed, uint64_t n, int w,
                                 const uint32_t* h_lo, const uint32_t* h_hi, int K, int tail_granule,
                                 void* h_out, uint64_t* h_counts);

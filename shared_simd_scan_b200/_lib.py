@@ -13,6 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libsss_b200.so")
 
 SSS_MAX_PREDICATES = 1024
+TAIL_EXACT, TAIL_8, TAIL_32, TAIL_CURSOR32, TAIL_CURSOR64 = 1, 8, 32, 132, 164
 
 # every symbol include/sss_b200.h declares: name -> (restype, argtypes)
 _vp, _u64, _u32, _i, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_size_t
@@ -25,6 +26,8 @@ SIGNATURES = {
     "sss_packed_bytes": (_sz, [_u64, _i]),
     "sss_unpack_bytes": (_sz, [_u64]),
     "sss_bitvec_bytes": (_sz, [_u64]),
+    "sss_tail_eval_codes": (_u64, [_u64, _i, _i]),
+    "sss_tail_out_bytes": (_u64, [_u64, _i, _i]),
     "sss_pack": (_i, [_vp, _vp, _u64, _i, _vp, _vp]),
     "sss_generate_packed": (_i, [_vp, _vp, _u64, _i, _u64, _u64, _vp]),
     "sss_unpack": (_i, [_vp, _vp, _u64, _i, _vp, _vp]),
@@ -35,6 +38,7 @@ SIGNATURES = {
     "sss_host_unpack": (_i, [_vp, _vp, _u64, _i, _vp]),
     "sss_host_scan_range": (_i, [_vp, _vp, _u64, _i, _u32, _u32, _i, _vp, _vp]),
     "sss_host_shared_scan": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _i, _i, _vp, _u64, _vp]),
+    "sss_host_shared_scan_ptrs": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "sss_host_shared_scan_linear": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "sss_host_pack": (_i, [_vp, _vp, _u64, _i, _vp]),
     "sss_host_alloc": (_vp, [_sz]),

@@ -75,8 +75,48 @@ int check_common(const sss_ctx* ctx, const void* packed, int w)
 
 int check_k(int K) { return (K < 1 || K > SSS_MAX_PREDICATES) ? SSS_ERR_INVALID_ARG : SSS_OK; }
 
-uint64_t out_bytes_for(uint64_t n, int granule) { return granule == 32 ? 4 * ((n + 31) / 32) : (n + 7) / 8; }
-uint64_t eval_codes_for(uint64_t n, int granule) { return granule <= 1 ? n : round_up_u64(n, (uint64_t)granule); }
+// Tail modes (SSS_TAIL_*).  The cursor modes restate how far the reference's word-cursor loops run:
+// scan_unvectorized walks ceil(w*n/64) 64-bit words and also evaluates a code that merely STARTS in
+// the last word (reference src/simd_scan.cpp:25,39-91), leaving early once `oi == input_size`
+// compares its output BYTE index with the code count (:58); shared_scan_*_parallel does the same
+// over 32-bit words and 4-byte flushes (reference src/simd_scan_shared.cpp:160,184-266,219).
+bool tail_mode_ok(int g)
+{
+    return g == SSS_TAIL_EXACT || g == SSS_TAIL_8 || g == SSS_TAIL_32 || g == SSS_TAIL_CURSOR32 ||
+           g == SSS_TAIL_CURSOR64;
+}
+
+uint64_t eval_codes_for(uint64_t n, int w, int g)
+{
+    if (n == 0) return 0;
+    const uint64_t bits = n * (uint64_t)w;
+    switch (g) {
+        case SSS_TAIL_EXACT: return n;
+        case SSS_TAIL_8: return round_up_u64(n, 8);
+        case SSS_TAIL_32: return round_up_u64(n, 32);
+        case SSS_TAIL_CURSOR64: {
+            const uint64_t span = round_up_u64(bits, 64);
+            return std::min((span + w - 1) / w, 8 * n);
+        }
+        case SSS_TAIL_CURSOR32: {
+            const uint64_t span = round_up_u64(bits, 32);
+            return std::min((span + w - 1) / w, 32 * ((n + 3) / 4));
+        }
+    }
+    return 0;
+}
+
+uint64_t out_bytes_for(uint64_t n, int w, int g)
+{
+    switch (g) {
+        case SSS_TAIL_EXACT:
+        case SSS_TAIL_8: return (n + 7) / 8;
+        case SSS_TAIL_32: return 4 * ((n + 31) / 32);
+        case SSS_TAIL_CURSOR64: return (eval_codes_for(n, w, g) + 7) / 8;
+        case SSS_TAIL_CURSOR32: return 4 * ((eval_codes_for(n, w, g) + 31) / 32);
+    }
+    return 0;
+}
 
 // codes per staged chunk: a multiple of 1024 codes (=> whole words in, whole words out, 16-byte
 // aligned packed offsets for every width)
@@ -163,6 +203,16 @@ int sss_ctx_sm_count(const sss_ctx* ctx) { return ctx ? ctx->dev.sm_count : 0; }
 size_t sss_packed_bytes(uint64_t n, int w) { return (size_t)(packed_payload_bytes(n, w) + 256); }
 size_t sss_unpack_bytes(uint64_t n) { return (size_t)(n * 4 + 32); }
 size_t sss_bitvec_bytes(uint64_t n) { return (size_t)((n + 7) / 8 + 32); }
+
+uint64_t sss_tail_eval_codes(uint64_t n, int w, int tail_granule)
+{
+    return (w < 1 || w > 32 || !tail_mode_ok(tail_granule)) ? 0 : eval_codes_for(n, w, tail_granule);
+}
+
+uint64_t sss_tail_out_bytes(uint64_t n, int w, int tail_granule)
+{
+    return (w < 1 || w > 32 || !tail_mode_ok(tail_granule)) ? 0 : out_bytes_for(n, w, tail_granule);
+}
 
 // ---- device-resident entry points ----------------------------------------------------------
 
@@ -307,10 +357,10 @@ int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, u
                         int tail_granule, void* h_bitvec, uint64_t* h_count)
 {
     if (ctx == nullptr || h_packed == nullptr || h_bitvec == nullptr || w < 1 || w > 32) return SSS_ERR_INVALID_ARG;
-    if (tail_granule != 1 && tail_granule != 8 && tail_granule != 32) return SSS_ERR_INVALID_ARG;
+    if (!tail_mode_ok(tail_granule)) return SSS_ERR_INVALID_ARG;
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
-    const uint64_t n_eval = eval_codes_for(n, tail_granule);
-    const uint64_t out_total = out_bytes_for(n, tail_granule);
+    const uint64_t n_eval = eval_codes_for(n, w, tail_granule);
+    const uint64_t out_total = out_bytes_for(n, w, tail_granule);
     const uint64_t C = chunk_codes(w / 8.0, 1 / 8.0);
     SSS_CK(cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned long long), ctx->slots[0].stream));
     SSS_CK(cudaStreamSynchronize(ctx->slots[0].stream));
@@ -335,18 +385,19 @@ int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, u
 }
 
 static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uint64_t n, int w, const uint32_t* h_lo,
-                            const uint32_t* h_hi, int K, int tail_granule, void* h_out, uint64_t stride_bytes,
-                            uint64_t* h_counts)
+                            const uint32_t* h_hi, int K, int tail_granule, void* h_out, void* const* h_out_ptrs,
+                            uint64_t stride_bytes, uint64_t* h_counts)
 {
-    if (ctx == nullptr || h_packed == nullptr || h_out == nullptr || h_lo == nullptr || h_hi == nullptr)
+    if (ctx == nullptr || h_packed == nullptr || (h_out == nullptr && h_out_ptrs == nullptr) || h_lo == nullptr ||
+        h_hi == nullptr)
         return SSS_ERR_INVALID_ARG;
     if (w < 1 || w > 32) return SSS_ERR_INVALID_ARG;
     SSS_TRY(check_k(K));
-    if (tail_granule != 1 && tail_granule != 8 && tail_granule != 32) return SSS_ERR_INVALID_ARG;
+    if (!tail_mode_ok(tail_granule)) return SSS_ERR_INVALID_ARG;
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
-    const uint64_t n_eval = eval_codes_for(n, tail_granule);
-    const uint64_t out_total = out_bytes_for(n, tail_granule);  // per predicate (bitvectors) / rows (linear)
-    if (!linear && stride_bytes < out_total) return SSS_ERR_INVALID_ARG;
+    const uint64_t n_eval = eval_codes_for(n, w, tail_granule);
+    const uint64_t out_total = out_bytes_for(n, w, tail_granule);  // per predicate (bitvectors) / rows (linear)
+    if (!linear && h_out_ptrs == nullptr && stride_bytes < out_total) return SSS_ERR_INVALID_ARG;
     const uint64_t C = chunk_codes(w / 8.0, K / 8.0);
     cudaStream_t s0 = ctx->slots[0].stream;
     SSS_CK(cudaMemcpyAsync(ctx->d_lo, h_lo, (size_t)K * 4, cudaMemcpyHostToDevice, s0));
@@ -370,6 +421,11 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
         if (linear) {
             SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_out) + out_off * (uint64_t)K, s.d_out, piece * (uint64_t)K,
                                    cudaMemcpyDeviceToHost, s.stream));
+        } else if (h_out_ptrs != nullptr) {
+            for (int k = 0; k < K; k++)
+                SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_out_ptrs[k]) + out_off,
+                                       static_cast<uint8_t*>(s.d_out) + (uint64_t)k * chunk_stride, piece,
+                                       cudaMemcpyDeviceToHost, s.stream));
         } else {
             SSS_CK(cudaMemcpy2DAsync(static_cast<uint8_t*>(h_out) + out_off, stride_bytes, s.d_out, chunk_stride, piece,
                                      (size_t)K, cudaMemcpyDeviceToHost, s.stream));
@@ -384,13 +440,25 @@ int sss_host_shared_scan(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, 
                          const uint32_t* h_hi, int K, int tail_granule, void* h_bitvecs, uint64_t stride_bytes,
                          uint64_t* h_counts)
 {
-    return host_shared_impl(ctx, false, h_packed, n, w, h_lo, h_hi, K, tail_granule, h_bitvecs, stride_bytes, h_counts);
+    return host_shared_impl(ctx, false, h_packed, n, w, h_lo, h_hi, K, tail_granule, h_bitvecs, nullptr, stride_bytes,
+                            h_counts);
+}
+
+int sss_host_shared_scan_ptrs(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, const uint32_t* h_lo,
+                              const uint32_t* h_hi, int K, int tail_granule, void* const* h_bitvec_ptrs,
+                              uint64_t* h_counts)
+{
+    if (h_bitvec_ptrs == nullptr) return SSS_ERR_INVALID_ARG;
+    for (int k = 0; k < K && k < SSS_MAX_PREDICATES; k++)
+        if (h_bitvec_ptrs[k] == nullptr) return SSS_ERR_INVALID_ARG;
+    return host_shared_impl(ctx, false, h_packed, n, w, h_lo, h_hi, K, tail_granule, nullptr, h_bitvec_ptrs, 0,
+                            h_counts);
 }
 
 int sss_host_shared_scan_linear(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, const uint32_t* h_lo,
                                 const uint32_t* h_hi, int K, int tail_granule, void* h_out, uint64_t* h_counts)
 {
-    return host_shared_impl(ctx, true, h_packed, n, w, h_lo, h_hi, K, tail_granule, h_out, 0, h_counts);
+    return host_shared_impl(ctx, true, h_packed, n, w, h_lo, h_hi, K, tail_granule, h_out, nullptr, 0, h_counts);
 }
 
 int sss_host_pack(sss_ctx* ctx, const uint32_t* h_codes, uint64_t n, int w, void* h_packed)

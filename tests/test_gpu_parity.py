@@ -228,3 +228,34 @@ def test_full_size_properties(sss, w):
     re = sss.compress(dec, w)
     payload = n2 * w // 8
     assert torch.equal(re[:payload], d_packed[:payload])
+
+
+def test_range_shards_concatenate_to_the_whole(sss):
+    """The multi-GPU contract on one GPU: shards cut at multiples of 128 codes, scanned
+    independently from sub-buffers of the column, concatenate to the single-GPU result; counts add;
+    positions rebased by the shard base are globally ascending."""
+    from shared_simd_scan_b200 import dist as sdist
+    w, n, world = 23, 1_000_003, 4
+    codes, packed = column(n, w, seed=23)
+    d_packed = dev(packed)
+    m = (1 << w) - 1
+    lo, hi = m // 7, m // 3
+    whole, cnt = sss.scan(d_packed, n, w, lo, hi)
+    pieces, total, allpos = [], 0, []
+    for r in range(world):
+        first, count = sdist.shard_range(n, world, r)
+        assert first % 128 == 0
+        sub = torch.zeros(sss.packed_bytes(count, w), dtype=torch.uint8, device="cuda")
+        nb = (count * w + 7) // 8
+        sub[:nb] = d_packed[first * w // 8: first * w // 8 + nb]
+        if (count * w) % 8:  # clear the bits of the next shard's first code in the last byte
+            sub[nb - 1] &= (1 << ((count * w) % 8)) - 1
+        bv, c = sss.scan(sub, count, w, lo, hi)
+        pieces.append(host(bv)[: (count + 7) // 8])
+        total += int(c.item())
+        pos, num = sss.positions(bv, count, base=first)
+        allpos.append(host(pos)[: int(num.item())])
+    assert total == int(cnt.item())
+    assert (np.concatenate(pieces)[: (n + 7) // 8] == host(whole)[: (n + 7) // 8]).all()
+    pos, num = sss.positions(whole, n)
+    assert (np.concatenate(allpos) == host(pos)[: int(num.item())]).all()
