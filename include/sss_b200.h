@@ -15,7 +15,8 @@
  *  - Bitvector: bit i%8 of byte i/8 is the predicate on code i (src/simd_scan.cpp:48-52,
  *    src/util.cpp:51-58).  Device entry points write whole 32-bit words, 4*ceil(n/32) bytes,
  *    with bits >= n cleared; buffers are sized with sss_bitvec_bytes(n) (= scan_output_buffer_size,
- *    src/simd_scan.hpp:35-40) and must be 4-byte aligned (16 for shard slices).
+ *    src/simd_scan.hpp:35-40) and must be 16-byte aligned (any cudaMalloc pointer, and any shard
+ *    slice that starts at a multiple of 128 codes).
  *  - Predicates are inclusive unsigned ranges lo <= code <= hi.  The reference's equality scan
  *    (`decompressed_element == predicate_key`, src/simd_scan.cpp:47) is lo == hi == key.
  *    lo > hi, or lo >= 2^w, matches nothing.

@@ -264,7 +264,7 @@ int sss_scan_range(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32
                    uint64_t* d_count, void* stream)
 {
     SSS_TRY(check_common(ctx, d_packed, w));
-    if (d_bitvec == nullptr || (reinterpret_cast<uintptr_t>(d_bitvec) & 3)) return SSS_ERR_INVALID_ARG;
+    if (d_bitvec == nullptr || (reinterpret_cast<uintptr_t>(d_bitvec) & 15)) return SSS_ERR_INVALID_ARG;
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return scan_range_impl(ctx, d_packed, n, w, lo, hi, d_bitvec, reinterpret_cast<unsigned long long*>(d_count), true,
                            static_cast<cudaStream_t>(stream));

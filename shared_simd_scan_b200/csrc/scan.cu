@@ -2,15 +2,24 @@
 //
 // Replaces scan_unvectorized / scan_128 / scan_128_unrolled / scan_256 / scan_256_unrolled
 // (reference src/simd_scan.cpp:20-306).  Those walk the column 8 or 32 codes at a time with
-// pshufb + pand + pcmpeqd + movmskps; here each thread owns one 32-code block (= W consecutive
-// 32-bit words = one 32-bit word of the result bitvector, the same unit scan_*_unrolled writes,
-// src/simd_scan.cpp:183,211), extracts every code LEFT-aligned with one funnel shift whose
-// distance is a compile-time constant, and evaluates lo <= code <= hi as one subtract + one
-// unsigned compare (see sss::aligned_range).  Decoded codes never leave registers.
+// pshufb + pand + pcmpeqd + movmskps; here each thread owns 32-code blocks (= W consecutive 32-bit
+// words = one 32-bit word of the result bitvector, the same unit scan_*_unrolled writes,
+// src/simd_scan.cpp:183,211) and evaluates lo <= code <= hi on them without ever materialising the
+// decoded codes in memory.  Three evaluators, chosen per width at compile time:
+//
+//   W = 1        the predicate is a boolean function of the bit itself: one LOP3 per 32 codes
+//   W = 2..12    word-parallel compare on the packed words (swar.cuh): ~8W/32 instructions per code;
+//                these widths are integer-issue bound, not HBM bound, with a per-code pipeline
+//   W = 13..32   per-code pipeline: one funnel shift with a compile-time distance moves the code
+//                LEFT-aligned into a register, then one subtract + one unsigned compare
+//                (sss::aligned_range); already at the HBM roofline for these widths
 //
 // Data movement: persistent CTAs stream contiguous tiles of the packed column into a shared-memory
-// ring with TMA bulk copies (common.cuh TileRing); lanes write consecutive result words, so every
-// warp store is one full 128-byte line.
+// ring with TMA bulk copies (common.cuh TileRing).  A thread reads its blocks from shared memory
+// with the widest conflict-free access for its width (128-bit loads over 1-4 blocks whose chunk
+// stride is odd; for W = 8/16/32, where the stride is a power of two, each lane starts at a
+// different 16-byte chunk of its block and the result word is rotated back with one funnel shift).
+// Lanes write consecutive result words, so every warp store covers whole 128-byte lines.
 //
 // Roofline: HBM.  Algorithmic bytes per code = W/8 (packed input) + 1/8 (bitvector).
 #include <array>
@@ -18,18 +27,41 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "swar.cuh"
 
 namespace sss {
 
+enum ScanMode : int { kScalar = 0, kSwarLoTop0 = 1, kSwarLoTop1 = 2, kOneBit = 3 };
+
 template <int W>
-struct ScanCfg {
-    // 32-code blocks per thread per tile: keeps tiles at 16-32 KB for every width
-    static constexpr int kR = (W <= 1) ? 16 : (W <= 2) ? 8 : (W <= 5) ? 4 : (W <= 10) ? 2 : 1;
-    static constexpr int kBlocksPerTile = kThreads * kR;  // = result words per tile
+struct ScanPlan {
+    static constexpr bool kSwar = (W >= 2 && W <= 12);
+    static constexpr bool kRot = (W == 8 || W == 16 || W == 32);
+    // 128-bit shared-memory loads (group of kG blocks per thread, kG*W a multiple of 4 words)
+    static constexpr bool kVec = (W == 1) || kRot || (kSwar && W != 9 && W != 11);
+    static constexpr int kG = !kVec ? 1 : (W == 1 ? 4 : (W % 4 == 0 ? 1 : (W % 2 == 0 ? 2 : 4)));
+    static constexpr int kGroupWords = kG * W;
+    static constexpr int kR = (16 / kGroupWords) > 1 ? (16 / kGroupWords) : 1;  // groups per thread per tile
+    static constexpr int kBlocksPerTile = kThreads * kR * kG;                    // = result words per tile
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
     static constexpr int kStages = (kTileBytes > 24 * 1024) ? 3 : 4;
     using Ring = TileRing<kTileBytes, kStages>;
 };
+
+struct ScalarArgs {
+    uint32_t lo_al, span_al;
+};
+struct OneBitArgs {
+    uint32_t flip, all;  // result = (x ^ flip) | all
+};
+template <int W>
+struct ScanArgs {
+    ScalarArgs scalar;
+    OneBitArgs onebit;
+    std::conditional_t<(W >= 2 && W <= 16), SwarConsts<(W >= 2 && W <= 16) ? W : 2>, ScalarArgs> swar;
+};
+
+// ---- per-code evaluator (W >= 13) -----------------------------------------------------------------
 
 template <int W, int J>
 struct EvalBlock {
@@ -44,37 +76,108 @@ struct EvalBlock<W, 32> {
     static __device__ __forceinline__ uint32_t run(const uint32_t (&)[W], uint32_t, uint32_t) { return 0u; }
 };
 
-template <int W>
-__global__ void __launch_bounds__(kThreads, 2)
-scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n, uint32_t lo_al,
-                  uint32_t span_al, uint32_t* __restrict__ bitvec, unsigned long long* __restrict__ count)
+template <int W, int kMode>
+__device__ __forceinline__ uint32_t eval_block(const uint32_t (&x)[W], const ScanArgs<W>& a)
 {
-    using Cfg = ScanCfg<W>;
+    if constexpr (kMode == kOneBit) {
+        return (x[0] ^ a.onebit.flip) | a.onebit.all;
+    } else if constexpr (kMode == kScalar) {
+        return EvalBlock<W, 0>::run(x, a.scalar.lo_al, a.scalar.span_al);
+    } else {
+        return swar_eval_block<W, kMode == kSwarLoTop1>(x, a.swar);
+    }
+}
+
+// ---- shared memory -> registers ---------------------------------------------------------------------
+
+// lane-dependent starting chunk for the power-of-two strides (see file header)
+template <int W>
+__device__ __forceinline__ uint32_t rot_chunks()
+{
+    const uint32_t lane = threadIdx.x & 31;
+    if constexpr (W == 32) return lane & 7;
+    if constexpr (W == 16) return (lane >> 1) & 3;
+    if constexpr (W == 8) return (lane >> 2) & 1;
+    return 0;
+}
+
+// words of thread group `tg` (kG consecutive blocks) -> x[kG][W]
+template <int W>
+__device__ __forceinline__ void load_group(const uint32_t* buf, uint32_t tg, uint32_t (&x)[ScanPlan<W>::kG][W],
+                                           uint32_t rot)
+{
+    using P = ScanPlan<W>;
+    if constexpr (P::kVec) {
+        constexpr int chunks = P::kGroupWords / 4;
+        const uint4* src = reinterpret_cast<const uint4*>(buf) + (size_t)tg * chunks;
+        uint32_t* flat = &x[0][0];
+#pragma unroll
+        for (int q = 0; q < chunks; q++) {
+            int c = q;
+            if constexpr (P::kRot) c = (q + rot) & (chunks - 1);
+            const uint4 v = src[c];
+            flat[4 * q + 0] = v.x;
+            flat[4 * q + 1] = v.y;
+            flat[4 * q + 2] = v.z;
+            flat[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; k++) x[0][k] = buf[(size_t)tg * W + k];
+    }
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+
+template <int W, int kMode>
+__global__ void __launch_bounds__(kThreads, 2)
+scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
+                  const __grid_constant__ ScanArgs<W> args, uint32_t* __restrict__ bitvec,
+                  unsigned long long* __restrict__ count)
+{
+    using P = ScanPlan<W>;
     extern __shared__ __align__(128) uint8_t smem[];
-    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    typename P::Ring ring(smem, packed, readable_bytes16);
     ring.start();
 
     const uint64_t n_blocks = (n + 31) >> 5;  // result words
     const uint32_t tail_bits = (uint32_t)(n & 31);
+    const uint32_t rot = rot_chunks<W>();
     uint32_t hits = 0;
 
     uint32_t iter = 0;
     for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
         ring.wait(iter);
-        const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
-        const uint64_t tile_block0 = tile * (uint64_t)Cfg::kBlocksPerTile;
+        const uint32_t* buf = ring.stage_words(iter % P::kStages);
+        const uint64_t tile_block0 = tile * (uint64_t)P::kBlocksPerTile;
 #pragma unroll
-        for (int r = 0; r < Cfg::kR; r++) {
-            const uint32_t b = r * kThreads + threadIdx.x;
-            const uint64_t gb = tile_block0 + b;
-            if (gb < n_blocks) {
-                uint32_t x[W];
+        for (int r = 0; r < P::kR; r++) {
+            const uint32_t tg = r * kThreads + threadIdx.x;
+            const uint64_t gb0 = tile_block0 + (uint64_t)tg * P::kG;
+            if (gb0 < n_blocks) {
+                uint32_t x[P::kG][W];
+                load_group<W>(buf, tg, x, rot);
+                uint32_t res[P::kG];
 #pragma unroll
-                for (int k = 0; k < W; k++) x[k] = buf[b * W + k];
-                uint32_t res = EvalBlock<W, 0>::run(x, lo_al, span_al);
-                if (tail_bits != 0 && gb == n_blocks - 1) res &= (1u << tail_bits) - 1u;
-                hits += __popc(res);
-                st_stream_u32(bitvec + gb, res);
+                for (int b = 0; b < P::kG; b++) {
+                    uint32_t v = eval_block<W, kMode>(x[b], args);
+                    if constexpr (P::kRot) v = __funnelshift_l(v, v, rot * (128 / W));
+                    if (tail_bits != 0 && gb0 + b == n_blocks - 1) v &= (1u << tail_bits) - 1u;
+                    if (gb0 + b >= n_blocks) v = 0;
+                    hits += __popc(v);
+                    res[b] = v;
+                }
+                uint32_t* dst = bitvec + gb0;
+                if (P::kG == 4 && gb0 + 4 <= n_blocks) {
+                    __stcs(reinterpret_cast<uint4*>(dst),
+                           make_uint4(res[0], res[1 % P::kG], res[2 % P::kG], res[3 % P::kG]));
+                } else if (P::kG == 2 && gb0 + 2 <= n_blocks) {
+                    __stcs(reinterpret_cast<uint2*>(dst), make_uint2(res[0], res[1 % P::kG]));
+                } else {
+#pragma unroll
+                    for (int b = 0; b < P::kG; b++)
+                        if (gb0 + b < n_blocks) st_stream_u32(dst + b, res[b]);
+                }
             }
         }
         ring.release(iter, tile);
@@ -82,28 +185,53 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
     if (count != nullptr) cta_add_u64(hits, count);
 }
 
-template <int W>
-static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, AlignedRange r, uint32_t* bitvec,
-                            unsigned long long* count, cudaStream_t stream)
+// ---- launch ---------------------------------------------------------------------------------------
+
+template <int W, int kMode>
+static cudaError_t launch_mode(const Device& dev, const void* packed, uint64_t n, const ScanArgs<W>& args,
+                               uint32_t* bitvec, unsigned long long* count, cudaStream_t stream)
 {
-    using Cfg = ScanCfg<W>;
-    constexpr int smem = Cfg::Ring::kSmemBytes;
+    using P = ScanPlan<W>;
+    constexpr int smem = P::Ring::kSmemBytes;
     static bool configured[64] = {};
     if (!configured[dev.ordinal & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(scan_range_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e =
+            cudaFuncSetAttribute(scan_range_kernel<W, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured[dev.ordinal & 63] = true;
     }
     const uint64_t n_blocks = (n + 31) / 32;
     const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
-    const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
+    const uint64_t tiles = (readable + P::kTileBytes - 1) / P::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    scan_range_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, r.lo_al, r.span_al, bitvec, count);
+    scan_range_kernel<W, kMode><<<grid, kThreads, smem, stream>>>(packed, readable, n, args, bitvec, count);
     return cudaGetLastError();
 }
 
-using ScanLauncher = cudaError_t (*)(const Device&, const void*, uint64_t, AlignedRange, uint32_t*,
+template <int W>
+static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, uint32_t lo, uint32_t hi,
+                            uint32_t* bitvec, unsigned long long* count, cudaStream_t stream)
+{
+    // caller guarantees lo <= hi <= 2^W - 1 (non-empty range, already clamped)
+    ScanArgs<W> args{};
+    if constexpr (W == 1) {
+        args.onebit.flip = (lo == 0 && hi == 0) ? 0xFFFFFFFFu : 0u;
+        args.onebit.all = (lo == 0 && hi == 1) ? 0xFFFFFFFFu : 0u;
+        return launch_mode<W, kOneBit>(dev, packed, n, args, bitvec, count, stream);
+    } else if constexpr (ScanPlan<W>::kSwar) {
+        args.swar = make_swar_consts<W>(lo, hi);
+        if (args.swar.lo_top) return launch_mode<W, kSwarLoTop1>(dev, packed, n, args, bitvec, count, stream);
+        return launch_mode<W, kSwarLoTop0>(dev, packed, n, args, bitvec, count, stream);
+    } else {
+        const AlignedRange r = aligned_range(W, lo, hi);
+        args.scalar.lo_al = r.lo_al;
+        args.scalar.span_al = r.span_al;
+        return launch_mode<W, kScalar>(dev, packed, n, args, bitvec, count, stream);
+    }
+}
+
+using ScanLauncher = cudaError_t (*)(const Device&, const void*, uint64_t, uint32_t, uint32_t, uint32_t*,
                                      unsigned long long*, cudaStream_t);
 
 template <int... Ws>
@@ -116,7 +244,11 @@ cudaError_t launch_scan_range(const Device& dev, const void* packed, uint64_t n,
                               uint32_t* bitvec, unsigned long long* count, cudaStream_t stream)
 {
     static constexpr auto table = make_table(std::make_integer_sequence<int, 32>{});
-    return table[w - 1](dev, packed, n, r, bitvec, count, stream);
+    // recover the clamped code-domain bounds from the aligned form
+    const int s = 32 - w;
+    const uint32_t lo = r.lo_al >> s;
+    const uint32_t hi = (r.lo_al + r.span_al) >> s;
+    return table[w - 1](dev, packed, n, lo, hi, bitvec, count, stream);
 }
 
 }  // namespace sss
