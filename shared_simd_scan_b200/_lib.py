@@ -10,7 +10,8 @@ import os
 from functools import lru_cache
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libsss_b200.so")
+# SSS_LIB_PATH: developer override to A/B-test an experimental build of the same ABI
+LIB_PATH = os.environ.get("SSS_LIB_PATH") or os.path.join(PKG_DIR, "libsss_b200.so")
 
 SSS_MAX_PREDICATES = 1024
 TAIL_EXACT, TAIL_8, TAIL_32, TAIL_CURSOR32, TAIL_CURSOR64 = 1, 8, 32, 132, 164

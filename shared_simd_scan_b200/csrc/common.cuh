@@ -101,6 +101,18 @@ __device__ __forceinline__ void st_stream_v4(int4* p, int4 v) { __stcs(p, v); }
 // consume the tile from shared memory, meet at __syncthreads, and thread 0 refills the stage.
 //
 // Shared memory layout: [kStages][kTileBytes + kPadBytes] then kStages mbarriers.
+// Ring depth.  Measured on B200 (profiles/r01_ring_depth_ab.txt): with two CTAs per SM the scan
+// peaks with about 64 KB of ring per CTA (~100 KB of loads in flight per SM); deeper rings are
+// SLOWER (104 KB per CTA costs 5-10 % at W = 8..17), shallower ones starve.  2..8 stages.
+#ifndef SSS_RING_KB
+#define SSS_RING_KB 64
+#endif
+constexpr int ring_stages(int tile_bytes)
+{
+    const int fit = (SSS_RING_KB * 1024) / (tile_bytes + 16);
+    return fit < 2 ? 2 : (fit > 8 ? 8 : fit);
+}
+
 template <int kTileBytes, int kStages, int kPadBytes = 16>
 struct TileRing {
     static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");

@@ -24,7 +24,7 @@ template <int W>
 struct LinearCfg {
     static constexpr int kBlocksPerTile = kThreads;
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
-    static constexpr int kStages = 4;
+    static constexpr int kStages = ring_stages(kTileBytes);
     using Ring = TileRing<kTileBytes, kStages>;
     static constexpr int kPredSmem = 4 * SSS_MAX_K * 4;
     static constexpr int kSmemBytes = Ring::kSmemBytes + 8 + kPredSmem;

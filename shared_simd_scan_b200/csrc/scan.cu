@@ -41,11 +41,21 @@ struct ScanPlan {
     static constexpr bool kVec = (W == 1) || kRot || (kSwar && W != 9 && W != 11);
     static constexpr int kG = !kVec ? 1 : (W == 1 ? 4 : (W % 4 == 0 ? 1 : (W % 2 == 0 ? 2 : 4)));
     static constexpr int kGroupWords = kG * W;
-    static constexpr int kR = (16 / kGroupWords) > 1 ? (16 / kGroupWords) : 1;  // groups per thread per tile
-    static constexpr int kBlocksPerTile = kThreads * kR * kG;                    // = result words per tile
+#ifndef SSS_SCAN_TILE_WORDS
+#define SSS_SCAN_TILE_WORDS 16  // target words per thread per tile (x 1 KiB = tile bytes)
+#endif
+#ifndef SSS_SCAN_MAX_CTAS
+#define SSS_SCAN_MAX_CTAS 2
+#endif
+    static constexpr int kR =
+        (SSS_SCAN_TILE_WORDS / kGroupWords) > 1 ? (SSS_SCAN_TILE_WORDS / kGroupWords) : 1;  // groups per thread per tile
+    static constexpr int kBlocksPerTile = kThreads * kR * kG;                                // = result words per tile
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
-    static constexpr int kStages = (kTileBytes > 24 * 1024) ? 3 : 4;
+    static constexpr int kStages = ring_stages(kTileBytes);
     using Ring = TileRing<kTileBytes, kStages>;
+    // resident CTAs per SM: as many as shared memory allows (227 KB usable, 1 KB reserved per CTA)
+    static constexpr int kFit = (227 * 1024) / (Ring::kSmemBytes + 1024 + 64);
+    static constexpr int kCtasPerSm = kFit < 1 ? 1 : (kFit > SSS_SCAN_MAX_CTAS ? SSS_SCAN_MAX_CTAS : kFit);
 };
 
 struct ScalarArgs {
@@ -129,8 +139,50 @@ __device__ __forceinline__ void load_group(const uint32_t* buf, uint32_t tg, uin
 
 // ---- the kernel ---------------------------------------------------------------------------------
 
+// One tile.  kChecked = false is the hot path (every block of the tile holds 32 valid codes: no
+// bounds or tail handling, 32-bit indexing); kChecked = true handles the last, ragged tile.
+template <int W, int kMode, bool kChecked>
+__device__ __forceinline__ uint32_t scan_tile(const uint32_t* buf, const ScanArgs<W>& args, uint32_t rot,
+                                              uint32_t* __restrict__ tile_out, uint64_t blocks_left,
+                                              uint32_t tail_bits)
+{
+    using P = ScanPlan<W>;
+    uint32_t hits = 0;
+#pragma unroll
+    for (int r = 0; r < P::kR; r++) {
+        const uint32_t tg = r * kThreads + threadIdx.x;
+        const uint32_t b0 = tg * P::kG;  // first block of this group, relative to the tile
+        if (kChecked && b0 >= blocks_left) continue;
+        uint32_t x[P::kG][W];
+        load_group<W>(buf, tg, x, rot);
+        uint32_t res[P::kG];
+#pragma unroll
+        for (int b = 0; b < P::kG; b++) {
+            uint32_t v = eval_block<W, kMode>(x[b], args);
+            if constexpr (P::kRot) v = __funnelshift_l(v, v, rot * (128 / W));
+            if constexpr (kChecked) {
+                if (tail_bits != 0 && b0 + b == blocks_left - 1) v &= (1u << tail_bits) - 1u;
+                if (b0 + b >= blocks_left) v = 0;
+            }
+            hits += __popc(v);
+            res[b] = v;
+        }
+        uint32_t* dst = tile_out + b0;
+        if (P::kG == 4 && (!kChecked || b0 + 4 <= blocks_left)) {
+            __stcs(reinterpret_cast<uint4*>(dst), make_uint4(res[0], res[1 % P::kG], res[2 % P::kG], res[3 % P::kG]));
+        } else if (P::kG == 2 && (!kChecked || b0 + 2 <= blocks_left)) {
+            __stcs(reinterpret_cast<uint2*>(dst), make_uint2(res[0], res[1 % P::kG]));
+        } else {
+#pragma unroll
+            for (int b = 0; b < P::kG; b++)
+                if (!kChecked || b0 + b < blocks_left) st_stream_u32(dst + b, res[b]);
+        }
+    }
+    return hits;
+}
+
 template <int W, int kMode>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, ScanPlan<W>::kCtasPerSm)
 scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                   const __grid_constant__ ScanArgs<W> args, uint32_t* __restrict__ bitvec,
                   unsigned long long* __restrict__ count)
@@ -141,6 +193,7 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
     ring.start();
 
     const uint64_t n_blocks = (n + 31) >> 5;  // result words
+    const uint64_t full_blocks = n >> 5;      // blocks whose 32 codes are all valid
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const uint32_t rot = rot_chunks<W>();
     uint32_t hits = 0;
@@ -150,35 +203,11 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
         ring.wait(iter);
         const uint32_t* buf = ring.stage_words(iter % P::kStages);
         const uint64_t tile_block0 = tile * (uint64_t)P::kBlocksPerTile;
-#pragma unroll
-        for (int r = 0; r < P::kR; r++) {
-            const uint32_t tg = r * kThreads + threadIdx.x;
-            const uint64_t gb0 = tile_block0 + (uint64_t)tg * P::kG;
-            if (gb0 < n_blocks) {
-                uint32_t x[P::kG][W];
-                load_group<W>(buf, tg, x, rot);
-                uint32_t res[P::kG];
-#pragma unroll
-                for (int b = 0; b < P::kG; b++) {
-                    uint32_t v = eval_block<W, kMode>(x[b], args);
-                    if constexpr (P::kRot) v = __funnelshift_l(v, v, rot * (128 / W));
-                    if (tail_bits != 0 && gb0 + b == n_blocks - 1) v &= (1u << tail_bits) - 1u;
-                    if (gb0 + b >= n_blocks) v = 0;
-                    hits += __popc(v);
-                    res[b] = v;
-                }
-                uint32_t* dst = bitvec + gb0;
-                if (P::kG == 4 && gb0 + 4 <= n_blocks) {
-                    __stcs(reinterpret_cast<uint4*>(dst),
-                           make_uint4(res[0], res[1 % P::kG], res[2 % P::kG], res[3 % P::kG]));
-                } else if (P::kG == 2 && gb0 + 2 <= n_blocks) {
-                    __stcs(reinterpret_cast<uint2*>(dst), make_uint2(res[0], res[1 % P::kG]));
-                } else {
-#pragma unroll
-                    for (int b = 0; b < P::kG; b++)
-                        if (gb0 + b < n_blocks) st_stream_u32(dst + b, res[b]);
-                }
-            }
+        uint32_t* tile_out = bitvec + tile_block0;
+        if (tile_block0 + P::kBlocksPerTile <= full_blocks) {
+            hits += scan_tile<W, kMode, false>(buf, args, rot, tile_out, 0, 0);
+        } else {
+            hits += scan_tile<W, kMode, true>(buf, args, rot, tile_out, n_blocks - tile_block0, tail_bits);
         }
         ring.release(iter, tile);
     }
@@ -203,7 +232,7 @@ static cudaError_t launch_mode(const Device& dev, const void* packed, uint64_t n
     const uint64_t n_blocks = (n + 31) / 32;
     const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
     const uint64_t tiles = (readable + P::kTileBytes - 1) / P::kTileBytes;
-    const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
+    const uint64_t max_ctas = (uint64_t)dev.sm_count * P::kCtasPerSm;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     scan_range_kernel<W, kMode><<<grid, kThreads, smem, stream>>>(packed, readable, n, args, bitvec, count);
     return cudaGetLastError();

@@ -22,7 +22,7 @@ template <int W>
 struct SharedCfg {
     static constexpr int kBlocksPerTile = kThreads;  // one 32-code block per thread per tile
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
-    static constexpr int kStages = 4;
+    static constexpr int kStages = ring_stages(kTileBytes);
     using Ring = TileRing<kTileBytes, kStages>;
     static constexpr int kPredSmem = 3 * SSS_MAX_K * 4 + SSS_MAX_K * 4;  // lo_al, span_al, valid, counts
     static constexpr int kSmemBytes = Ring::kSmemBytes + 8 /*align*/ + kPredSmem;

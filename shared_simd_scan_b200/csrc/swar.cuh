@@ -166,6 +166,26 @@ __device__ __forceinline__ uint32_t swar_eval_block(const uint32_t (&x)[W], cons
         constexpr uint32_t H = swar_hmask(W, i);
         swar_sub_word<W, i>(g[i], c.dh[i], t[i] & ~H);
     });
+    if constexpr (W == 2) {
+        // 16 result bits per word at stride 2: the multiply-gather moves only 2 bits at a time here,
+        // so interleave the two words' results (word 0 -> even bits, word 1 -> odd bits) and undo the
+        // interleave with the 4-step inverse perfect shuffle (even bits -> low half, odd -> high half)
+        uint32_t r[2];
+        static_for<0, 2>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr uint32_t H = 0xAAAAAAAAu;
+            const uint32_t v = kLoTop ? ((t[i] ^ x[i]) | ~H) : ((t[i] ^ x[i] ^ H) | ~H);
+            const uint32_t d = c.drh[i];
+            r[i] = (d & ~v) | (~(d ^ v) & g[i]);
+        });
+        uint32_t z = (r[0] >> 1) | r[1];
+        uint32_t u;
+        u = (z ^ (z >> 1)) & 0x22222222u; z = z ^ u ^ (u << 1);
+        u = (z ^ (z >> 2)) & 0x0C0C0C0Cu; z = z ^ u ^ (u << 2);
+        u = (z ^ (z >> 4)) & 0x00F000F0u; z = z ^ u ^ (u << 4);
+        u = (z ^ (z >> 8)) & 0x0000FF00u; z = z ^ u ^ (u << 8);
+        return z;
+    }
     uint32_t res = 0;
     static_for<0, W>([&](auto rc) {
         constexpr int i = W - 1 - decltype(rc)::value;  // highest word first: code 0 must end at bit 0

@@ -23,7 +23,7 @@ struct UnpackCfg {
     static constexpr int kR = 8;                                             // 4-code groups per thread per tile
     static constexpr int kCodesPerTile = kThreads * kCodesPerThread * kR;    // 8192
     static constexpr int kTileBytes = kCodesPerTile / 32 * W * 4;            // 1 KB * W
-    static constexpr int kStages = 4;
+    static constexpr int kStages = ring_stages(kTileBytes);
     using Ring = TileRing<kTileBytes, kStages>;
 };
 
