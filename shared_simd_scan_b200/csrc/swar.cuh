@@ -21,8 +21,8 @@
 // gathered to the top of the product by a constant whose partial products never collide, valid for
 // groups of at most W bits) and shifted into the result word with one funnel shift per group.
 //
-// Cost per word: 6 ALU ops + (1 IMAD + 1 SHF [+1 LOP]) per gather group, i.e. about 8W/32
-// instructions per code instead of ~4.  tools/swar_model.py is the executable model of exactly
+// Cost per word: 6 ALU ops + (1 IMAD + 1 SHF) per gather group, i.e. about 8W/32 instructions per
+// code instead of ~4.  tools/swar_model.py is the executable model of exactly
 // these operations and checks them against brute force for every width.
 #pragma once
 
@@ -198,8 +198,11 @@ __device__ __forceinline__ uint32_t swar_eval_block(const uint32_t (&x)[W], cons
         static_for<0, ng>([&](auto gc) {
             constexpr int gi = ng - 1 - decltype(gc)::value;
             constexpr SwarGroup grp = swar_group(W, i, gi);
-            const uint32_t sel = (ng == 1) ? r : (r & grp.mask);
-            res = __funnelshift_l(sel * grp.magic, res, grp.count);
+            // no pre-mask: result bit i times magic term k lands at 32-count+k+W*(i-first-k); for
+            // i-first-k > 0 that is past bit 31 (dropped), for < 0 it is below the window and all
+            // such positions are distinct (|k-k'| < W), so nothing collides with or carries into
+            // the top `count` bits
+            res = __funnelshift_l(r * grp.magic, res, grp.count);
         });
     });
     return res;

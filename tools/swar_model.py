@@ -75,7 +75,7 @@ def swar_block(x, W, lo, hi):
         R = ((DRH[i] & ~V) | (~(DRH[i] ^ V) & G[i])) & M32
         assert R & L == 0
         for (mask, magic, m) in reversed(groups[i]):
-            prod = ((R & mask) * magic) & M32
+            prod = (R * magic) & M32  # no pre-mask: partial products of other result bits never reach the window
             res = ((res << m) | (prod >> (32 - m))) & M32
     return res
 
