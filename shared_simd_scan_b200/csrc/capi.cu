@@ -50,6 +50,7 @@ struct sss_ctx {
     unsigned long long* d_counts = nullptr;  // SSS_MAX_PREDICATES + 1
     void* d_ws = nullptr;                    // positions workspace
     size_t ws_cap = 0;
+    void* d_index = nullptr;                 // predicate index of the shared scan in flight (predindex.cuh)
 };
 
 namespace {
@@ -173,6 +174,7 @@ int sss_ctx_create(int device, sss_ctx** out)
     cudaError_t e = cudaMalloc(&ctx->d_lo, SSS_MAX_PREDICATES * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_hi, SSS_MAX_PREDICATES * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counts, (SSS_MAX_PREDICATES + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_index, pred_index_bytes());
     if (e != cudaSuccess) {
         sss_ctx_destroy(ctx);
         return cuda_status(e);
@@ -194,6 +196,7 @@ int sss_ctx_destroy(sss_ctx* ctx)
     if (ctx->d_hi) cudaFree(ctx->d_hi);
     if (ctx->d_counts) cudaFree(ctx->d_counts);
     if (ctx->d_ws) cudaFree(ctx->d_ws);
+    if (ctx->d_index) cudaFree(ctx->d_index);
     delete ctx;
     return SSS_OK;
 }
@@ -288,17 +291,29 @@ int sss_positions(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base,
                                         reinterpret_cast<unsigned long long*>(d_num), ctx->d_ws, st));
 }
 
-static int shared_impl(sss_ctx* ctx, bool linear, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo,
-                       const uint32_t* d_hi, int K, void* d_out, uint64_t stride_bytes, unsigned long long* d_counts,
-                       bool zero_counts, cudaStream_t st)
+// One shared scan = build the predicate index, run the scan (which fills the index's interval
+// histogram), turn the histogram into per-predicate counts.  The index lives in the context, so a
+// context serves one shared scan at a time (calls on one stream serialise naturally).
+static int shared_scan_body(sss_ctx* ctx, bool linear, const void* d_packed, uint64_t n, int w, int K, void* d_out,
+                            uint64_t stride_bytes, bool count_matches, cudaStream_t st)
 {
-    if (d_counts && zero_counts) SSS_CK(cudaMemsetAsync(d_counts, 0, (size_t)K * sizeof(unsigned long long), st));
     if (n == 0) return SSS_OK;
     if (linear)
-        return cuda_status(
-            launch_shared_scan_linear(ctx->dev, d_packed, n, w, d_lo, d_hi, K, static_cast<uint8_t*>(d_out), d_counts, st));
-    return cuda_status(launch_shared_scan(ctx->dev, d_packed, n, w, d_lo, d_hi, K, static_cast<uint32_t*>(d_out),
-                                          stride_bytes / 4, d_counts, st));
+        return cuda_status(launch_shared_scan_linear(ctx->dev, d_packed, n, w, ctx->d_index, K,
+                                                     static_cast<uint8_t*>(d_out), count_matches, st));
+    return cuda_status(launch_shared_scan(ctx->dev, d_packed, n, w, ctx->d_index, K, static_cast<uint32_t*>(d_out),
+                                          stride_bytes / 4, count_matches, st));
+}
+
+static int shared_impl(sss_ctx* ctx, bool linear, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo,
+                       const uint32_t* d_hi, int K, void* d_out, uint64_t stride_bytes, unsigned long long* d_counts,
+                       cudaStream_t st)
+{
+    if (d_counts) SSS_CK(cudaMemsetAsync(d_counts, 0, (size_t)K * sizeof(unsigned long long), st));
+    SSS_CK(launch_build_pred_index(d_lo, d_hi, K, w, ctx->d_index, st));
+    SSS_TRY(shared_scan_body(ctx, linear, d_packed, n, w, K, d_out, stride_bytes, d_counts != nullptr, st));
+    if (d_counts) SSS_CK(launch_counts_from_histogram(ctx->d_index, K, d_counts, st));
+    return SSS_OK;
 }
 
 int sss_shared_scan(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo, const uint32_t* d_hi,
@@ -311,7 +326,7 @@ int sss_shared_scan(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, const
         return SSS_ERR_INVALID_ARG;
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return shared_impl(ctx, false, d_packed, n, w, d_lo, d_hi, K, d_bitvecs, stride_bytes,
-                       reinterpret_cast<unsigned long long*>(d_counts), true, static_cast<cudaStream_t>(stream));
+                       reinterpret_cast<unsigned long long*>(d_counts), static_cast<cudaStream_t>(stream));
 }
 
 int sss_shared_scan_linear(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo,
@@ -322,7 +337,7 @@ int sss_shared_scan_linear(sss_ctx* ctx, const void* d_packed, uint64_t n, int w
     if (d_lo == nullptr || d_hi == nullptr || d_out == nullptr) return SSS_ERR_INVALID_ARG;
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return shared_impl(ctx, true, d_packed, n, w, d_lo, d_hi, K, d_out, 0,
-                       reinterpret_cast<unsigned long long*>(d_counts), true, static_cast<cudaStream_t>(stream));
+                       reinterpret_cast<unsigned long long*>(d_counts), static_cast<cudaStream_t>(stream));
 }
 
 // ---- host-buffer entry points ----------------------------------------------------------------
@@ -403,6 +418,7 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
     SSS_CK(cudaMemcpyAsync(ctx->d_lo, h_lo, (size_t)K * 4, cudaMemcpyHostToDevice, s0));
     SSS_CK(cudaMemcpyAsync(ctx->d_hi, h_hi, (size_t)K * 4, cudaMemcpyHostToDevice, s0));
     SSS_CK(cudaMemsetAsync(ctx->d_counts, 0, (size_t)K * sizeof(unsigned long long), s0));
+    SSS_CK(launch_build_pred_index(ctx->d_lo, ctx->d_hi, K, w, ctx->d_index, s0));
     SSS_CK(cudaStreamSynchronize(s0));
     int slot = 0;
     for (uint64_t first = 0; first < n_eval; first += C, slot = (slot + 1) % kSlots) {
@@ -414,8 +430,7 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
         const uint8_t* src = static_cast<const uint8_t*>(h_packed) + first * (uint64_t)w / 8;
         SSS_CK(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
         const uint64_t chunk_stride = C / 8;  // device-side bitvector stride inside the slot
-        SSS_TRY(shared_impl(ctx, linear, s.d_in, cnt, w, ctx->d_lo, ctx->d_hi, K, s.d_out, chunk_stride, ctx->d_counts,
-                            false, s.stream));
+        SSS_TRY(shared_scan_body(ctx, linear, s.d_in, cnt, w, K, s.d_out, chunk_stride, h_counts != nullptr, s.stream));
         const uint64_t out_off = first / 8;  // bytes per predicate / rows already produced
         const uint64_t piece = std::min<uint64_t>(4 * ((cnt + 31) / 32), out_total - out_off);
         if (linear) {
@@ -432,7 +447,11 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
         }
     }
     for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
-    if (h_counts) SSS_CK(cudaMemcpy(h_counts, ctx->d_counts, (size_t)K * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (h_counts) {
+        SSS_CK(launch_counts_from_histogram(ctx->d_index, K, ctx->d_counts, s0));
+        SSS_CK(cudaMemcpyAsync(h_counts, ctx->d_counts, (size_t)K * sizeof(uint64_t), cudaMemcpyDeviceToHost, s0));
+        SSS_CK(cudaStreamSynchronize(s0));
+    }
     return SSS_OK;
 }
 

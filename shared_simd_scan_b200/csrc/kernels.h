@@ -24,15 +24,19 @@ cudaError_t launch_scan_range(const Device& dev, const void* packed, uint64_t n,
 cudaError_t launch_unpack(const Device& dev, const void* packed, uint64_t n, int w, int32_t* out,
                           cudaStream_t stream);
 
-// shared.cu -- K predicates in one pass -> K bitvectors (+K counts)
-cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n, int w, const uint32_t* lo,
-                               const uint32_t* hi, int K, uint32_t* bitvecs, uint64_t stride_words,
-                               unsigned long long* counts, cudaStream_t stream);
+// predindex.cu -- the K bounds compiled into a lookup structure (see predindex.cuh)
+size_t pred_index_bytes();
+cudaError_t launch_build_pred_index(const uint32_t* d_lo, const uint32_t* d_hi, int K, int w, void* d_index,
+                                    cudaStream_t stream);
+cudaError_t launch_counts_from_histogram(void* d_index, int K, unsigned long long* d_counts, cudaStream_t stream);
 
-// linear.cu -- K predicates in one pass -> [ceil(n/8)][K] byte matrix (+K counts)
-cudaError_t launch_shared_scan_linear(const Device& dev, const void* packed, uint64_t n, int w,
-                                      const uint32_t* lo, const uint32_t* hi, int K, uint8_t* out,
-                                      unsigned long long* counts, cudaStream_t stream);
+// shared.cu -- K predicates in one pass -> K bitvectors; match counts go to the index's histogram
+cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n, int w, const void* index, int K,
+                               uint32_t* bitvecs, uint64_t stride_words, bool count_matches, cudaStream_t stream);
+
+// linear.cu -- K predicates in one pass -> [4*ceil(n/32)][K] byte matrix
+cudaError_t launch_shared_scan_linear(const Device& dev, const void* packed, uint64_t n, int w, const void* index,
+                                      int K, uint8_t* out, bool count_matches, cudaStream_t stream);
 
 // pack.cu -- compressor and synthetic-column generator
 cudaError_t launch_pack(const Device& dev, const uint32_t* codes, uint64_t n, int w, uint32_t* packed,

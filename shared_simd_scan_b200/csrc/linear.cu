@@ -6,9 +6,13 @@
 // src/simd_scan.hpp:122-236).  The layout is pinned by the reference's only shared-scan unit test
 // (test/simd_scan_tests.cpp:108-150).
 //
-// A thread owns one 32-code block = 4 output rows.  For four predicates at a time it builds the four
-// 32-bit result words, regroups their bytes with PRMT into one 4-byte piece per row and stores it,
-// so every store covers 4 consecutive bytes of a K-byte row.
+// Same predicate index as shared.cu (predindex.cuh): a code is mapped to its precomputed K-bit match
+// row.  A thread owns one 32-code block = 4 output rows; for every column of 32 predicates it loads
+// the 32 rows' words and runs a 5-stage exchange network in registers -- three bit stages (8x8 bit
+// transposes inside every byte lane of every 8-register group) and two byte stages (PRMT) -- whose
+// result registers ARE the output: 8 registers per row, each holding 4 consecutive predicate bytes.
+// That is the same instruction count as the 32x32 transpose of shared.cu; the linear layout costs
+// nothing extra.  Every row piece a thread writes is 32 contiguous bytes (one full sector).
 //
 // Roofline: HBM.  Algorithmic bytes per code = W/8 + K/8.
 #include <array>
@@ -16,7 +20,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
-#include "predicates.cuh"
+#include "predindex.cuh"
 
 namespace sss {
 
@@ -26,34 +30,88 @@ struct LinearCfg {
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
     static constexpr int kStages = ring_stages(kTileBytes);
     using Ring = TileRing<kTileBytes, kStages>;
-    static constexpr int kPredSmem = 4 * SSS_MAX_K * 4;
-    static constexpr int kSmemBytes = Ring::kSmemBytes + 8 + kPredSmem;
+    static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
 };
 
-__device__ __forceinline__ uint32_t eval_word(const uint32_t (&t)[32], uint32_t lo_al, uint32_t span_al)
+constexpr int kLinCounterBytes = (kMaxBp + 1 + 3) / 4 * 16;
+
+template <int W, int J>
+struct LinRowOffsets {
+    static __device__ __forceinline__ void run(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&off)[32])
+    {
+        off[J] = mask_row_offset<W>(ix, left_aligned_code<W, J>(x));
+        LinRowOffsets<W, J + 1>::run(x, ix, off);
+    }
+};
+template <int W>
+struct LinRowOffsets<W, 32> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32]) {}
+};
+
+// in : a[8i + e] byte p bit f  = predicate 8p+f on code 8i+e           (i = row, e = code in group)
+// out: a[8i + 4*f2 + p] byte (f & 3) bit e, f2 = f >> 2                 = row i, bytes 8p+4*f2 .. +3
+// i.e. output word q (predicates 4q..4q+3) of row i is a[8i + 4*(q & 1) + (q >> 1)].
+__device__ __forceinline__ void exchange_linear(uint32_t (&a)[32])
 {
-    uint32_t res = 0;
 #pragma unroll
-    for (int j = 0; j < 32; j++) res |= ((t[j] - lo_al) <= span_al ? 1u : 0u) << j;
-    return res;
+    for (int g = 0; g < 32; g += 8)
+#pragma unroll
+        for (int k = g; k < g + 4; k++) {  // e2 <-> f2
+            const uint32_t lo = a[k], hi = a[k + 4];
+            a[k] = (lo & 0x0F0F0F0Fu) | ((hi << 4) & 0xF0F0F0F0u);
+            a[k + 4] = ((lo >> 4) & 0x0F0F0F0Fu) | (hi & 0xF0F0F0F0u);
+        }
+#pragma unroll
+    for (int g = 0; g < 32; g += 4)
+#pragma unroll
+        for (int k = g; k < g + 2; k++) {  // e1 <-> f1
+            const uint32_t lo = a[k], hi = a[k + 2];
+            a[k] = (lo & 0x33333333u) | ((hi << 2) & 0xCCCCCCCCu);
+            a[k + 2] = ((lo >> 2) & 0x33333333u) | (hi & 0xCCCCCCCCu);
+        }
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {  // e0 <-> f0
+        const uint32_t lo = a[k], hi = a[k + 1];
+        a[k] = (lo & 0x55555555u) | ((hi << 1) & 0xAAAAAAAAu);
+        a[k + 1] = ((lo >> 1) & 0x55555555u) | (hi & 0xAAAAAAAAu);
+    }
+    // now a[8i + f] byte p bit e.  Byte stages: register bit f1 <-> byte-index bit p1, then f0 <-> p0
+#pragma unroll
+    for (int g = 0; g < 32; g += 4)
+#pragma unroll
+        for (int k = g; k < g + 2; k++) {
+            const uint32_t lo = a[k], hi = a[k + 2];
+            a[k] = __byte_perm(lo, hi, 0x5410);
+            a[k + 2] = __byte_perm(lo, hi, 0x7632);
+        }
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+        const uint32_t lo = a[k], hi = a[k + 1];
+        a[k] = __byte_perm(lo, hi, 0x6240);
+        a[k + 1] = __byte_perm(lo, hi, 0x7351);
+    }
 }
 
 template <int W>
 __global__ void __launch_bounds__(kThreads, 2)
 shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
-                          const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, int K,
-                          uint8_t* __restrict__ out, unsigned long long* __restrict__ counts)
+                          const uint8_t* __restrict__ g_index, int K, bool masks_in_smem, uint8_t* __restrict__ out,
+                          bool count_matches)
 {
     using Cfg = LinearCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
-    PredicateTable preds(smem + ((Cfg::Ring::kSmemBytes + 15) & ~15));
-    preds.load(W, lo, hi, K);
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);  // per-CTA interval histogram
+    for (int i = threadIdx.x; i < 2 * K + 1; i += kThreads) s_hist[i] = 0;
+    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kLinCounterBytes, masks_in_smem);
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();
 
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
-    const uint32_t lane = threadIdx.x & 31;
+    const int cols = (K + 31) >> 5;
+    const uint8_t* mask_base = reinterpret_cast<const uint8_t*>(ix.masks);
+    // widest store the row pitch K and the base alignment allow
+    const bool vec16 = (K & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const bool vec4 = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
 
     uint32_t iter = 0;
@@ -62,81 +120,96 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
         const bool active = gb < n_blocks;
-        uint32_t t[32];
+        uint32_t off[32];
+        uint32_t valid = 32;  // valid codes of this block
         if (active) {
             uint32_t x[W];
 #pragma unroll
             for (int k = 0; k < W; k++) x[k] = buf[threadIdx.x * W + k];
-            LeftAlignAll<W, 0>::run(x, t);
-        }
-        const uint32_t keep = (active && tail_bits != 0 && gb == n_blocks - 1) ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
-        uint8_t* row0 = out + gb * 4 * (uint64_t)K;  // rows 4*gb .. 4*gb+3
-        if (vec4) {
-            for (int k = 0; k < K; k += 4) {
-                uint32_t r[4] = {0, 0, 0, 0};
-                if (active) {
+            LinRowOffsets<W, 0>::run(x, ix, off);
+            if (tail_bits != 0 && gb == n_blocks - 1) valid = tail_bits;
+            if (count_matches) {
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        r[q] = eval_word(t, preds.lo_al[k + q], preds.span_al[k + q]) & preds.valid[k + q] & keep;
-                    // byte i of r[q] is row i, predicate k+q  ->  one word per row
-                    const uint32_t a01 = __byte_perm(r[0], r[1], 0x5140);  // r0.b0 r1.b0 r0.b1 r1.b1
-                    const uint32_t a23 = __byte_perm(r[2], r[3], 0x5140);
-                    const uint32_t b01 = __byte_perm(r[0], r[1], 0x7362);  // r0.b2 r1.b2 r0.b3 r1.b3
-                    const uint32_t b23 = __byte_perm(r[2], r[3], 0x7362);
-                    uint32_t* p = reinterpret_cast<uint32_t*>(row0 + k);
-                    const uint64_t rs = (uint64_t)K / 4;
-                    __stcs(p, __byte_perm(a01, a23, 0x5410));
-                    __stcs(p + rs, __byte_perm(a01, a23, 0x7632));
-                    __stcs(p + 2 * rs, __byte_perm(b01, b23, 0x5410));
-                    __stcs(p + 3 * rs, __byte_perm(b01, b23, 0x7632));
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, __popc(r[q]));
-                    if (lane == 0 && c) atomicAdd(&preds.counts[k + q], c);
-                }
+                for (int j = 0; j < 32; j++)
+                    if ((uint32_t)j < valid) atomicAdd(&s_hist[off[j] >> ix.row_shift], 1u);
             }
         } else {
-            for (int k = 0; k < K; k++) {
-                uint32_t r = 0;
-                if (active) {
-                    r = eval_word(t, preds.lo_al[k], preds.span_al[k]) & preds.valid[k] & keep;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) row0[(uint64_t)i * K + k] = (uint8_t)(r >> (8 * i));
+            for (int j = 0; j < 32; j++) off[j] = 0;
+        }
+        uint8_t* row0 = out + gb * 4 * (uint64_t)K;  // rows 4*gb .. 4*gb+3
+        for (int c = 0; c < cols; c++) {
+            uint32_t m[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                m[j] = *reinterpret_cast<const uint32_t*>(mask_base + off[j] + 4 * c);
+                if ((uint32_t)j >= valid) m[j] = 0;  // codes past n contribute zero bits
+            }
+            exchange_linear(m);
+            const int kk = K - 32 * c;  // predicates in this column
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint8_t* dst = row0 + (uint64_t)i * K + 32 * c;
+                    // word q of the row = m[8i + 4*(q&1) + (q>>1)]
+                    const uint32_t w0 = m[8 * i + 0], w1 = m[8 * i + 4], w2 = m[8 * i + 1], w3 = m[8 * i + 5];
+                    const uint32_t w4 = m[8 * i + 2], w5 = m[8 * i + 6], w6 = m[8 * i + 3], w7 = m[8 * i + 7];
+                    if (vec16 && kk >= 32) {
+                        __stcs(reinterpret_cast<uint4*>(dst), make_uint4(w0, w1, w2, w3));
+                        __stcs(reinterpret_cast<uint4*>(dst) + 1, make_uint4(w4, w5, w6, w7));
+                    } else {
+                        const uint32_t ws[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            if (4 * q + 4 <= kk && vec4) {
+                                __stcs(reinterpret_cast<uint32_t*>(dst) + q, ws[q]);
+                            } else {
+#pragma unroll
+                                for (int b = 0; b < 4; b++)
+                                    if (4 * q + b < kk) dst[4 * q + b] = (uint8_t)(ws[q] >> (8 * b));
+                            }
+                        }
+                    }
                 }
-                const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, __popc(r));
-                if (lane == 0 && c) atomicAdd(&preds.counts[k], c);
             }
         }
         ring.release(iter, tile);
     }
-    preds.flush_counts(counts, K);
+    __syncthreads();
+    if (count_matches) {
+        unsigned long long* g_hist =
+            reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(g_index) + PredIndexLayout::kHist);
+        for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += kThreads)
+            if (s_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)s_hist[i]);
+    }
 }
 
 template <int W>
-static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const uint32_t* lo, const uint32_t* hi,
-                            int K, uint8_t* out, unsigned long long* counts, cudaStream_t stream)
+static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K, uint8_t* out,
+                            bool count_matches, cudaStream_t stream)
 {
     using Cfg = LinearCfg<W>;
-    constexpr int smem = Cfg::kSmemBytes;
-    static bool configured[64] = {};
-    if (!configured[dev.ordinal & 63]) {
-        cudaError_t e =
-            cudaFuncSetAttribute(shared_scan_linear_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    bool masks_in_smem = false;
+    const size_t smem = Cfg::kRingBytes + kLinCounterBytes + pred_index_smem_bytes(K, W, &masks_in_smem) + 64;
+    static size_t configured[64] = {};
+    if (configured[dev.ordinal & 63] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(shared_scan_linear_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
         if (e != cudaSuccess) return e;
-        configured[dev.ordinal & 63] = true;
+        configured[dev.ordinal & 63] = smem;
     }
     const uint64_t n_blocks = (n + 31) / 32;
     const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_linear_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, lo, hi, K, out, counts);
+    shared_scan_linear_kernel<W><<<grid, kThreads, smem, stream>>>(
+        packed, readable, n, static_cast<const uint8_t*>(index), K, masks_in_smem, out, count_matches);
     return cudaGetLastError();
 }
 
-using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const uint32_t*, const uint32_t*, int,
-                                 uint8_t*, unsigned long long*, cudaStream_t);
+using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, uint8_t*, bool,
+                                 cudaStream_t);
 
 template <int... Ws>
 static constexpr auto make_table(std::integer_sequence<int, Ws...>)
@@ -144,12 +217,11 @@ static constexpr auto make_table(std::integer_sequence<int, Ws...>)
     return std::array<Launcher, sizeof...(Ws)>{&launch_w<Ws + 1>...};
 }
 
-cudaError_t launch_shared_scan_linear(const Device& dev, const void* packed, uint64_t n, int w, const uint32_t* lo,
-                                      const uint32_t* hi, int K, uint8_t* out, unsigned long long* counts,
-                                      cudaStream_t stream)
+cudaError_t launch_shared_scan_linear(const Device& dev, const void* packed, uint64_t n, int w, const void* index,
+                                      int K, uint8_t* out, bool count_matches, cudaStream_t stream)
 {
     static constexpr auto table = make_table(std::make_integer_sequence<int, 32>{});
-    return table[w - 1](dev, packed, n, lo, hi, K, out, counts, stream);
+    return table[w - 1](dev, packed, n, index, K, out, count_matches, stream);
 }
 
 }  // namespace sss

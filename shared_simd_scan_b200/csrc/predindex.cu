@@ -1,0 +1,201 @@
+// predindex.cu -- builds the predicate index (predindex.cuh) on the device: one CTA of 1024 threads.
+//
+//   1. every valid predicate contributes the breakpoints lo (if > 0) and hi+1 (if <= 2^W - 1)
+//   2. bitonic sort of the (<= 2048) breakpoints in shared memory, 64-bit keys (2^32 = "none")
+//   3. compaction of the distinct values (block prefix sum)
+//   4. mask rows: row i, predicate k  <-  lo_k <= start_i <= hi_k
+//   5. locator: direct lut (W <= 13) or 4096 buckets on the top 12 bits
+#include <algorithm>
+
+#include "predindex.cuh"
+
+namespace sss {
+
+constexpr int kBuildThreads = 1024;
+constexpr unsigned long long kNone = 1ull << 32;
+
+// number of breakpoints <= v  (bp sorted ascending, M entries)
+__device__ __forceinline__ uint32_t count_le(const uint32_t* bp, uint32_t M, unsigned long long v)
+{
+    uint32_t lo = 0, hi = M;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((unsigned long long)bp[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kBuildThreads, 1)
+build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, int K, int w,
+                        uint8_t* __restrict__ index)
+{
+    __shared__ unsigned long long keys[kMaxBp];
+    __shared__ uint32_t bp[kMaxBp];
+    __shared__ uint32_t s_lo[kMaxK], s_hi[kMaxK];  // clamped bounds; lo > hi marks an empty predicate
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_M;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t maxv = code_mask(w);
+
+    // 1. bounds -> candidate breakpoints
+    for (uint32_t k = tid; k < (uint32_t)kMaxK; k += kBuildThreads) {
+        unsigned long long b0 = kNone, b1 = kNone;
+        uint32_t l = 1, h = 0;
+        if (k < (uint32_t)K) {
+            l = lo[k];
+            h = hi[k];
+            if (l <= h && l <= maxv) {
+                if (h > maxv) h = maxv;
+                if (l > 0) b0 = l;
+                if (h < maxv) b1 = (unsigned long long)h + 1;
+            } else {
+                l = 1;
+                h = 0;
+            }
+        }
+        s_lo[k] = l;
+        s_hi[k] = h;
+        keys[2 * k] = b0;
+        keys[2 * k + 1] = b1;
+    }
+    __syncthreads();
+
+    // 2. bitonic sort, 2048 keys, 1024 threads (one compare-exchange each per step)
+    for (uint32_t size = 2; size <= (uint32_t)kMaxBp; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            const uint32_t pos = 2 * tid - (tid & (stride - 1));
+            const bool up = ((pos & size) == 0);
+            const unsigned long long a = keys[pos], b = keys[pos + stride];
+            if ((a > b) == up) {
+                keys[pos] = b;
+                keys[pos + stride] = a;
+            }
+            __syncthreads();
+        }
+    }
+
+    // 3. distinct values -> bp[0..M)
+    uint32_t flags[2], incl;
+    {
+        uint32_t c = 0;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const uint32_t i = 2 * tid + e;
+            const bool first = keys[i] != kNone && (i == 0 || keys[i] != keys[i - 1]);
+            flags[e] = first ? 1u : 0u;
+            c += flags[e];
+        }
+        incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((tid & 31) >= (uint32_t)d) incl += o;
+        }
+        if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t t = warp_tot[tid], ti = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, ti, d);
+                if (tid >= (uint32_t)d) ti += o;
+            }
+            warp_tot[tid] = ti - t;
+            if (tid == 31) s_M = ti;
+        }
+        __syncthreads();
+        uint32_t at = warp_tot[tid >> 5] + incl - c;
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+            if (flags[e]) bp[at++] = (uint32_t)keys[2 * tid + e];
+    }
+    __syncthreads();
+    const uint32_t M = s_M;
+    uint32_t row_words = 1;
+    while (row_words < ((uint32_t)K + 31) / 32) row_words <<= 1;
+    const uint32_t row_shift = 31 - __clz(row_words * 4);
+
+    // header + thresholds of the left-aligned compare:  t >= bp << (32-W)  <=>  t > thr
+    if (tid == 0) {
+        PredIndexHeader* h = reinterpret_cast<PredIndexHeader*>(index + PredIndexLayout::kHeader);
+        h->num_bp = M;
+        h->row_words = row_words;
+        h->direct = (w <= kDirectMaxW) ? 1u : 0u;
+        h->K = (uint32_t)K;
+        h->w = (uint32_t)w;
+        h->row_shift = row_shift;
+    }
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(index + PredIndexLayout::kHist);
+    for (uint32_t i = tid; i <= M; i += kBuildThreads) hist[i] = 0;
+    uint32_t* thr = reinterpret_cast<uint32_t*>(index + PredIndexLayout::kThr);
+    for (uint32_t i = tid; i < M; i += kBuildThreads) thr[i] = (bp[i] << (32 - w)) - 1u;
+
+    // 4. mask rows
+    uint32_t* masks = reinterpret_cast<uint32_t*>(index + PredIndexLayout::kMasks);
+    const uint32_t total_words = (M + 1) * row_words;
+    for (uint32_t idx = tid; idx < total_words; idx += kBuildThreads) {
+        const uint32_t row = idx / row_words, c = idx - row * row_words;
+        const uint32_t start = row == 0 ? 0u : bp[row - 1];
+        uint32_t word = 0;
+#pragma unroll 4
+        for (uint32_t b = 0; b < 32; b++) {
+            const uint32_t k = c * 32 + b;  // k >= K: s_lo = 1 > s_hi = 0 -> never set
+            word |= ((s_lo[k] <= start && start <= s_hi[k]) ? 1u : 0u) << b;
+        }
+        masks[idx] = word;
+    }
+
+    // 5. locator
+    if (w <= kDirectMaxW) {
+        uint16_t* lut = reinterpret_cast<uint16_t*>(index + PredIndexLayout::kLocator);
+        for (uint32_t v = tid; v < (1u << w); v += kBuildThreads) lut[v] = (uint16_t)count_le(bp, M, v);
+    } else {
+        uint2* bucket = reinterpret_cast<uint2*>(index + PredIndexLayout::kLocator);
+        const int shift = w - kBucketBits;
+        for (uint32_t b = tid; b < (uint32_t)kBuckets; b += kBuildThreads) {
+            const unsigned long long start = (unsigned long long)b << shift;
+            const unsigned long long end = start + (1ull << shift) - 1;
+            const uint32_t first = start == 0 ? 0u : count_le(bp, M, start - 1);
+            const uint32_t cnt = count_le(bp, M, end) - first;
+            uint2 e;
+            e.x = cnt ? ((bp[first] << (32 - w)) - 1u) : 0xFFFFFFFFu;
+            e.y = first | (cnt << 16);
+            bucket[b] = e;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBuildThreads, 1)
+counts_from_histogram_kernel(uint8_t* __restrict__ index, int K, unsigned long long* __restrict__ counts)
+{
+    const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(index + PredIndexLayout::kHeader);
+    const uint32_t M = h->num_bp, row_words = h->row_words;
+    const uint32_t* masks = reinterpret_cast<const uint32_t*>(index + PredIndexLayout::kMasks);
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(index + PredIndexLayout::kHist);
+    for (uint32_t k = threadIdx.x; k < (uint32_t)K; k += kBuildThreads) {
+        unsigned long long c = 0;
+        for (uint32_t i = 0; i <= M; i++)
+            if ((masks[i * row_words + (k >> 5)] >> (k & 31)) & 1u) c += hist[i];
+        counts[k] += c;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= M; i += kBuildThreads) hist[i] = 0;
+}
+
+size_t pred_index_bytes() { return PredIndexLayout::kTotal; }
+
+cudaError_t launch_counts_from_histogram(void* d_index, int K, unsigned long long* d_counts, cudaStream_t stream)
+{
+    counts_from_histogram_kernel<<<1, kBuildThreads, 0, stream>>>(static_cast<uint8_t*>(d_index), K, d_counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_pred_index(const uint32_t* d_lo, const uint32_t* d_hi, int K, int w, void* d_index,
+                                    cudaStream_t stream)
+{
+    build_pred_index_kernel<<<1, kBuildThreads, 0, stream>>>(d_lo, d_hi, K, w, static_cast<uint8_t*>(d_index));
+    return cudaGetLastError();
+}
+
+}  // namespace sss

@@ -3,10 +3,14 @@
 //
 // Replaces shared_scan_128_standard / _standard_unrolled / _parallel / _sequential* / _threaded and
 // the 256-bit twins (reference src/simd_scan_shared.cpp:9-466).  Like shared_scan_128_standard
-// (:49-86) the column is decoded once and every predicate is evaluated against the decoded codes;
-// unlike it the unit of work is a 32-code block per thread, so each predicate's result is a whole
-// 32-bit word and lanes write consecutive words of the same bitvector (128-byte lines) instead of
-// the reference's K scattered single-byte stores (:82).
+// (:49-86) the column is decoded once for all predicates.  Unlike it, the predicates are not looped
+// over per code: the K bounds are compiled into a predicate index (predindex.cuh) that maps a code
+// to a precomputed K-bit row "which predicates match" with two shared-memory loads, and the
+// 32 codes x K bits a thread collects for its 32-code block are turned into K result words with
+// 32x32 bit-matrix transposes in registers.  Cost per code at K = 64: ~30 integer ops instead of
+// ~130 for the compare loop, which is what moves this kernel from issue-bound towards HBM-bound.
+// Each predicate's result is a whole 32-bit word per block and lanes write consecutive words of
+// the same bitvector (128-byte lines) instead of the reference's K scattered byte stores (:82).
 //
 // Roofline: HBM.  Algorithmic bytes per code = W/8 + K/8.
 #include <array>
@@ -14,7 +18,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
-#include "predicates.cuh"
+#include "predindex.cuh"
 
 namespace sss {
 
@@ -24,26 +28,44 @@ struct SharedCfg {
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
     static constexpr int kStages = ring_stages(kTileBytes);
     using Ring = TileRing<kTileBytes, kStages>;
-    static constexpr int kPredSmem = 3 * SSS_MAX_K * 4 + SSS_MAX_K * 4;  // lo_al, span_al, valid, counts
-    static constexpr int kSmemBytes = Ring::kSmemBytes + 8 /*align*/ + kPredSmem;
+    static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
+};
+
+constexpr int kCounterBytes = (kMaxBp + 1 + 3) / 4 * 16;  // up to 2K+1 uint32 interval counters, 16-byte multiple
+
+// mask-row offsets of the 32 codes of a block
+template <int W, int J>
+struct RowOffsets {
+    static __device__ __forceinline__ void run(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&off)[32])
+    {
+        off[J] = mask_row_offset<W>(ix, left_aligned_code<W, J>(x));
+        RowOffsets<W, J + 1>::run(x, ix, off);
+    }
+};
+template <int W>
+struct RowOffsets<W, 32> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32]) {}
 };
 
 template <int W>
 __global__ void __launch_bounds__(kThreads, 2)
 shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
-                   const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, int K,
-                   uint32_t* __restrict__ bitvecs, uint64_t stride_words, unsigned long long* __restrict__ counts)
+                   const uint8_t* __restrict__ g_index, int K, bool masks_in_smem, uint32_t* __restrict__ bitvecs,
+                   uint64_t stride_words, bool count_matches)
 {
     using Cfg = SharedCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
-    PredicateTable preds(smem + ((Cfg::Ring::kSmemBytes + 15) & ~15));
-    preds.load(W, lo, hi, K);
+    // per-CTA interval histogram (match counts are derived from it, see predindex.cuh)
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);
+    for (int i = threadIdx.x; i < 2 * K + 1; i += kThreads) s_hist[i] = 0;
+    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kCounterBytes, masks_in_smem);
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
-    ring.start();  // contains the __syncthreads that publishes the predicate table
+    ring.start();  // contains the __syncthreads that publishes the index and the zeroed counters
 
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
-    const uint32_t lane = threadIdx.x & 31;
+    const int cols = (K + 31) >> 5;
+    const uint8_t* mask_base = reinterpret_cast<const uint8_t*>(ix.masks);
 
     uint32_t iter = 0;
     for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
@@ -51,56 +73,71 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
         const bool active = gb < n_blocks;
-        uint32_t t[32];
+        uint32_t off[32];
         if (active) {
             uint32_t x[W];
 #pragma unroll
             for (int k = 0; k < W; k++) x[k] = buf[threadIdx.x * W + k];
-            LeftAlignAll<W, 0>::run(x, t);
+            RowOffsets<W, 0>::run(x, ix, off);
+            if (count_matches) {
+                const uint32_t valid = (tail_bits != 0 && gb == n_blocks - 1) ? tail_bits : 32u;
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if ((uint32_t)j < valid) atomicAdd(&s_hist[off[j] >> ix.row_shift], 1u);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) off[j] = 0;
         }
         const uint32_t keep = (active && tail_bits != 0 && gb == n_blocks - 1) ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
-        for (int k = 0; k < K; k++) {
-            uint32_t res = 0;
-            if (active) {
-                const uint32_t lo_al = preds.lo_al[k], span_al = preds.span_al[k];
+        for (int c = 0; c < cols; c++) {
+            uint32_t m[32];
 #pragma unroll
-                for (int j = 0; j < 32; j++) res |= ((t[j] - lo_al) <= span_al ? 1u : 0u) << j;
-                res &= preds.valid[k] & keep;
-                st_stream_u32(bitvecs + (uint64_t)k * stride_words + gb, res);
+            for (int j = 0; j < 32; j++) m[j] = *reinterpret_cast<const uint32_t*>(mask_base + off[j] + 4 * c);
+            transpose32(m);  // m[k'] bit j = predicate 32c+k' on code j
+            const int kk = K - 32 * c;  // predicates in this column (>= 32: full)
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                if (k < kk && active) st_stream_u32(bitvecs + (uint64_t)(32 * c + k) * stride_words + gb, m[k] & keep);
             }
-            const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, __popc(res));
-            if (lane == 0 && c) atomicAdd(&preds.counts[k], c);
         }
         ring.release(iter, tile);
     }
-    preds.flush_counts(counts, K);
+    __syncthreads();
+    if (count_matches) {
+        unsigned long long* g_hist =
+            reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(g_index) + PredIndexLayout::kHist);
+        for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += kThreads)
+            if (s_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)s_hist[i]);
+    }
 }
 
 template <int W>
-static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const uint32_t* lo, const uint32_t* hi,
-                            int K, uint32_t* bitvecs, uint64_t stride_words, unsigned long long* counts,
-                            cudaStream_t stream)
+static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K,
+                            uint32_t* bitvecs, uint64_t stride_words, bool count_matches, cudaStream_t stream)
 {
     using Cfg = SharedCfg<W>;
-    constexpr int smem = Cfg::kSmemBytes;
-    static bool configured[64] = {};
-    if (!configured[dev.ordinal & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(shared_scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    bool masks_in_smem = false;
+    const size_t smem = Cfg::kRingBytes + kCounterBytes + pred_index_smem_bytes(K, W, &masks_in_smem) + 64;
+    static size_t configured[64] = {};
+    if (configured[dev.ordinal & 63] < smem) {
+        cudaError_t e =
+            cudaFuncSetAttribute(shared_scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[dev.ordinal & 63] = true;
+        configured[dev.ordinal & 63] = smem;
     }
     const uint64_t n_blocks = (n + 31) / 32;
     const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, lo, hi, K, bitvecs, stride_words,
-                                                           counts);
+    shared_scan_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, static_cast<const uint8_t*>(index), K,
+                                                           masks_in_smem, bitvecs, stride_words, count_matches);
     return cudaGetLastError();
 }
 
-using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const uint32_t*, const uint32_t*, int,
-                                 uint32_t*, uint64_t, unsigned long long*, cudaStream_t);
+using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, uint32_t*, uint64_t, bool,
+                                 cudaStream_t);
 
 template <int... Ws>
 static constexpr auto make_table(std::integer_sequence<int, Ws...>)
@@ -108,12 +145,11 @@ static constexpr auto make_table(std::integer_sequence<int, Ws...>)
     return std::array<Launcher, sizeof...(Ws)>{&launch_w<Ws + 1>...};
 }
 
-cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n, int w, const uint32_t* lo,
-                               const uint32_t* hi, int K, uint32_t* bitvecs, uint64_t stride_words,
-                               unsigned long long* counts, cudaStream_t stream)
+cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n, int w, const void* index, int K,
+                               uint32_t* bitvecs, uint64_t stride_words, bool count_matches, cudaStream_t stream)
 {
     static constexpr auto table = make_table(std::make_integer_sequence<int, 32>{});
-    return table[w - 1](dev, packed, n, lo, hi, K, bitvecs, stride_words, counts, stream);
+    return table[w - 1](dev, packed, n, index, K, bitvecs, stride_words, count_matches, stream);
 }
 
 }  // namespace sss
