@@ -28,25 +28,13 @@ template <int W>
 struct LinearCfg {
     static constexpr int kBlocksPerTile = kThreads;
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
-    static constexpr int kStages = ring_stages(kTileBytes);
+    // compute-bound kernels: a shallow ring is enough and leaves shared memory for the mask table
+    static constexpr int kStages = kTileBytes >= 16 * 1024 ? 2 : 3;
     using Ring = TileRing<kTileBytes, kStages>;
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
 };
 
 constexpr int kLinCounterBytes = (kMaxBp + 1 + 3) / 4 * 16;
-
-template <int W, int J>
-struct LinRowOffsets {
-    static __device__ __forceinline__ void run(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&off)[32])
-    {
-        off[J] = mask_row_offset<W>(ix, left_aligned_code<W, J>(x));
-        LinRowOffsets<W, J + 1>::run(x, ix, off);
-    }
-};
-template <int W>
-struct LinRowOffsets<W, 32> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32]) {}
-};
 
 // in : a[8i + e] byte p bit f  = predicate 8p+f on code 8i+e           (i = row, e = code in group)
 // out: a[8i + 4*f2 + p] byte (f & 3) bit e, f2 = f >> 2                 = row i, bytes 8p+4*f2 .. +3
@@ -56,25 +44,13 @@ __device__ __forceinline__ void exchange_linear(uint32_t (&a)[32])
 #pragma unroll
     for (int g = 0; g < 32; g += 8)
 #pragma unroll
-        for (int k = g; k < g + 4; k++) {  // e2 <-> f2
-            const uint32_t lo = a[k], hi = a[k + 4];
-            a[k] = (lo & 0x0F0F0F0Fu) | ((hi << 4) & 0xF0F0F0F0u);
-            a[k + 4] = ((lo >> 4) & 0x0F0F0F0Fu) | (hi & 0xF0F0F0F0u);
-        }
+        for (int k = g; k < g + 4; k++) exchange_bits<4>(a[k], a[k + 4]);  // e2 <-> f2
 #pragma unroll
     for (int g = 0; g < 32; g += 4)
 #pragma unroll
-        for (int k = g; k < g + 2; k++) {  // e1 <-> f1
-            const uint32_t lo = a[k], hi = a[k + 2];
-            a[k] = (lo & 0x33333333u) | ((hi << 2) & 0xCCCCCCCCu);
-            a[k + 2] = ((lo >> 2) & 0x33333333u) | (hi & 0xCCCCCCCCu);
-        }
+        for (int k = g; k < g + 2; k++) exchange_bits<2>(a[k], a[k + 2]);  // e1 <-> f1
 #pragma unroll
-    for (int k = 0; k < 32; k += 2) {  // e0 <-> f0
-        const uint32_t lo = a[k], hi = a[k + 1];
-        a[k] = (lo & 0x55555555u) | ((hi << 1) & 0xAAAAAAAAu);
-        a[k + 1] = ((lo >> 1) & 0x55555555u) | (hi & 0xAAAAAAAAu);
-    }
+    for (int k = 0; k < 32; k += 2) exchange_bits<1>(a[k], a[k + 1]);      // e0 <-> f0
     // now a[8i + f] byte p bit e.  Byte stages: register bit f1 <-> byte-index bit p1, then f0 <-> p0
 #pragma unroll
     for (int g = 0; g < 32; g += 4)
@@ -92,24 +68,22 @@ __device__ __forceinline__ void exchange_linear(uint32_t (&a)[32])
     }
 }
 
-template <int W>
+template <int W, bool kSmem>
 __global__ void __launch_bounds__(kThreads, 2)
 shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
-                          const uint8_t* __restrict__ g_index, int K, bool masks_in_smem, uint8_t* __restrict__ out,
-                          bool count_matches)
+                          const uint8_t* __restrict__ g_index, int K, uint8_t* __restrict__ out, bool count_matches)
 {
     using Cfg = LinearCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);  // per-CTA interval histogram
     for (int i = threadIdx.x; i < 2 * K + 1; i += kThreads) s_hist[i] = 0;
-    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kLinCounterBytes, masks_in_smem);
+    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kLinCounterBytes, kSmem);
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();
 
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const int cols = (K + 31) >> 5;
-    const uint8_t* mask_base = reinterpret_cast<const uint8_t*>(ix.masks);
     // widest store the row pitch K and the base alignment allow
     const bool vec16 = (K & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const bool vec4 = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
@@ -119,35 +93,40 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
         ring.wait(iter);
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
-        const bool active = gb < n_blocks;
-        uint32_t off[32];
-        uint32_t valid = 32;  // valid codes of this block
-        if (active) {
-            uint32_t x[W];
+        if (gb < n_blocks) {
+            const bool last = tail_bits != 0 && gb == n_blocks - 1;  // the one ragged block of the column
+            uint32_t id[32];
+            {
+                uint32_t x[W];
 #pragma unroll
-            for (int k = 0; k < W; k++) x[k] = buf[threadIdx.x * W + k];
-            LinRowOffsets<W, 0>::run(x, ix, off);
-            if (tail_bits != 0 && gb == n_blocks - 1) valid = tail_bits;
+                for (int k = 0; k < W; k++) x[k] = buf[threadIdx.x * W + k];
+                block_ids<W>(x, ix, id);
+            }
             if (count_matches) {
+                if (!last) {
 #pragma unroll
-                for (int j = 0; j < 32; j++)
-                    if ((uint32_t)j < valid) atomicAdd(&s_hist[off[j] >> ix.row_shift], 1u);
+                    for (int j = 0; j < 32; j++) atomicAdd(&s_hist[id[j]], 1u);
+                } else {
+                    for (uint32_t j = 0; j < tail_bits; j++) {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int q = 0; q < 32; q++) v = (q == (int)j) ? id[q] : v;
+                        atomicAdd(&s_hist[v], 1u);
+                    }
+                }
             }
-        } else {
+            uint8_t* row0 = out + gb * 4 * (uint64_t)K;  // rows 4*gb .. 4*gb+3
+            for (int c = 0; c < cols; c++) {
+                uint32_t m[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) off[j] = 0;
-        }
-        uint8_t* row0 = out + gb * 4 * (uint64_t)K;  // rows 4*gb .. 4*gb+3
-        for (int c = 0; c < cols; c++) {
-            uint32_t m[32];
+                for (int j = 0; j < 32; j++) m[j] = mask_word<kSmem>(ix, id[j], c);
+                if (last) {  // codes past n contribute zero bits
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                m[j] = *reinterpret_cast<const uint32_t*>(mask_base + off[j] + 4 * c);
-                if ((uint32_t)j >= valid) m[j] = 0;  // codes past n contribute zero bits
-            }
-            exchange_linear(m);
-            const int kk = K - 32 * c;  // predicates in this column
-            if (active) {
+                    for (int j = 0; j < 32; j++)
+                        if ((uint32_t)j >= tail_bits) m[j] = 0;
+                }
+                exchange_linear(m);
+                const int kk = K - 32 * c;  // predicates in this column
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     uint8_t* dst = row0 + (uint64_t)i * K + 32 * c;
@@ -184,17 +163,15 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
     }
 }
 
-template <int W>
-static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K, uint8_t* out,
-                            bool count_matches, cudaStream_t stream)
+template <int W, bool kSmem>
+static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, const void* index, int K, uint8_t* out,
+                             bool count_matches, size_t smem, cudaStream_t stream)
 {
     using Cfg = LinearCfg<W>;
-    bool masks_in_smem = false;
-    const size_t smem = Cfg::kRingBytes + kLinCounterBytes + pred_index_smem_bytes(K, W, &masks_in_smem) + 64;
     static size_t configured[64] = {};
     if (configured[dev.ordinal & 63] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(shared_scan_linear_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(shared_scan_linear_kernel<W, kSmem>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev.ordinal & 63] = smem;
     }
@@ -203,9 +180,20 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, c
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_linear_kernel<W><<<grid, kThreads, smem, stream>>>(
-        packed, readable, n, static_cast<const uint8_t*>(index), K, masks_in_smem, out, count_matches);
+    shared_scan_linear_kernel<W, kSmem><<<grid, kThreads, smem, stream>>>(
+        packed, readable, n, static_cast<const uint8_t*>(index), K, out, count_matches);
     return cudaGetLastError();
+}
+
+template <int W>
+static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K, uint8_t* out,
+                            bool count_matches, cudaStream_t stream)
+{
+    bool masks_in_smem = false;
+    const size_t other = LinearCfg<W>::kRingBytes + kLinCounterBytes;
+    const size_t smem = other + pred_index_smem_bytes(K, W, other, &masks_in_smem) + 64;
+    if (masks_in_smem) return launch_ws<W, true>(dev, packed, n, index, K, out, count_matches, smem, stream);
+    return launch_ws<W, false>(dev, packed, n, index, K, out, count_matches, smem, stream);
 }
 
 using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, uint8_t*, bool,

@@ -112,9 +112,7 @@ build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restr
     }
     __syncthreads();
     const uint32_t M = s_M;
-    uint32_t row_words = 1;
-    while (row_words < ((uint32_t)K + 31) / 32) row_words <<= 1;
-    const uint32_t row_shift = 31 - __clz(row_words * 4);
+    const uint32_t row_words = (((uint32_t)K + 31) / 32) | 1u;  // odd stride, see pred_row_stride_words
 
     // header + thresholds of the left-aligned compare:  t >= bp << (32-W)  <=>  t > thr
     if (tid == 0) {
@@ -124,7 +122,7 @@ build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restr
         h->direct = (w <= kDirectMaxW) ? 1u : 0u;
         h->K = (uint32_t)K;
         h->w = (uint32_t)w;
-        h->row_shift = row_shift;
+        h->reserved = 0;
     }
     unsigned long long* hist = reinterpret_cast<unsigned long long*>(index + PredIndexLayout::kHist);
     for (uint32_t i = tid; i <= M; i += kBuildThreads) hist[i] = 0;
@@ -140,8 +138,8 @@ build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restr
         uint32_t word = 0;
 #pragma unroll 4
         for (uint32_t b = 0; b < 32; b++) {
-            const uint32_t k = c * 32 + b;  // k >= K: s_lo = 1 > s_hi = 0 -> never set
-            word |= ((s_lo[k] <= start && start <= s_hi[k]) ? 1u : 0u) << b;
+            const uint32_t k = c * 32 + b;  // K <= k < kMaxK: s_lo = 1 > s_hi = 0 -> never set
+            if (k < (uint32_t)kMaxK) word |= ((s_lo[k] <= start && start <= s_hi[k]) ? 1u : 0u) << b;
         }
         masks[idx] = word;
     }

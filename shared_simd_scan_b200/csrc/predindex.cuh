@@ -30,15 +30,16 @@ constexpr int kMaxBp = 2 * kMaxK;      // breakpoints
 constexpr int kDirectMaxW = 13;        // direct locator up to 2^13 code values
 constexpr int kBucketBits = 12;
 constexpr int kBuckets = 1 << kBucketBits;
-constexpr int kMaskSmemBytes = 16 * 1024;  // mask tables up to this size live in shared memory
+constexpr int kSharedSmemBudget = 112 * 1024;  // per CTA, two CTAs per SM: the mask table lives in shared
+                                               // memory whenever ring + counters + index fit in this
 
 struct PredIndexHeader {
     uint32_t num_bp;      // M
-    uint32_t row_words;   // ceil(K/32) rounded up to a power of two
+    uint32_t row_words;   // row stride in words: ceil(K/32) made odd
     uint32_t direct;      // 1: lut16 locator, 0: bucket locator
     uint32_t K;
     uint32_t w;
-    uint32_t row_shift;   // log2(row bytes)
+    uint32_t reserved;
     uint32_t pad[2];
 };
 
@@ -47,14 +48,11 @@ struct PredIndexHeader {
 // fall into each elementary INTERVAL (one shared-memory atomic per code, independent of K) and a
 // tiny epilogue kernel turns the interval histogram into per-predicate counts:
 //     count_k = sum over intervals i of hist[i] * mask[i][k].
-// Row sizes are rounded up to a power of two so that a row's byte offset shifts down to its id.
-inline uint32_t pred_row_words(int K)
-{
-    const uint32_t rw = ((uint32_t)K + 31) / 32;
-    uint32_t p = 1;
-    while (p < rw) p <<= 1;
-    return p;
-}
+//
+// Mask rows are stored with an ODD word stride: the 32 lanes of a warp read the same column of 32
+// different rows at once, and with a power-of-two stride (K = 1024: 32 words) every lane would hit
+// the same shared-memory bank.
+inline uint32_t pred_row_stride_words(int K) { return (((uint32_t)K + 31) / 32) | 1u; }
 
 // global-memory layout of the index (all offsets 16-byte aligned)
 struct PredIndexLayout {
@@ -63,7 +61,7 @@ struct PredIndexLayout {
     static constexpr size_t kLocator = kThr + (size_t)kMaxBp * 4;          // lut16[2^W] or uint2 bucket[4096]
     static constexpr size_t kLocatorBytes = (size_t)kBuckets * 8;          // 32 KB >= 2^13 * 2
     static constexpr size_t kMasks = kLocator + kLocatorBytes;             // uint32 mask[(M+1)][row_words]
-    static constexpr size_t kMasksBytes = (size_t)(kMaxBp + 1) * (kMaxK / 32) * 4;
+    static constexpr size_t kMasksBytes = ((size_t)(kMaxBp + 1) * (kMaxK / 32 + 1) * 4 + 255) / 256 * 256;
     static constexpr size_t kHist = kMasks + kMasksBytes + 256;            // unsigned long long hist[kMaxBp + 1]
     static constexpr size_t kTotal = kHist + (size_t)(kMaxBp + 1) * 8 + 256;
 };
@@ -79,22 +77,24 @@ struct PredIndexView {
     const uint32_t* thr;      // shared
     const void* locator;      // shared
     const uint32_t* masks;    // shared or global
-    uint32_t row_bytes;
-    uint32_t row_shift;
+    uint32_t masks_saddr;     // shared-window address of the mask table (when it lives in shared memory)
+    uint32_t row_words;
     uint32_t num_bp;
     bool direct;
 };
 
-// shared-memory bytes the kernels need for the index of this launch
-inline size_t pred_index_smem_bytes(int K, int w, bool* masks_in_smem)
+// shared-memory bytes the kernels need for the index of this launch; `other_bytes` is what the
+// kernel already uses (tile ring + interval counters)
+inline size_t pred_index_smem_bytes(int K, int w, size_t other_bytes, bool* masks_in_smem)
 {
-    const size_t row_words = pred_row_words(K);
+    const size_t stride = pred_row_stride_words(K);
     const size_t max_rows = (w >= 31) ? (size_t)(2 * K + 1) : std::min<size_t>((size_t)2 * K + 1, (size_t)1 << w);
-    const size_t mask_bytes = max_rows * row_words * 4;
-    *masks_in_smem = mask_bytes <= (size_t)kMaskSmemBytes;
+    const size_t mask_bytes = (max_rows * stride * 4 + 15) & ~(size_t)15;
     const size_t locator = (w <= kDirectMaxW) ? ((size_t)2 << w) : (size_t)kBuckets * 8;
     const size_t thr = (w <= kDirectMaxW) ? 0 : std::min<size_t>(2 * (size_t)K, kMaxBp) * 4;
-    return ((locator + 15) & ~(size_t)15) + ((thr + 15) & ~(size_t)15) + (*masks_in_smem ? ((mask_bytes + 15) & ~(size_t)15) : 0);
+    const size_t base = ((locator + 15) & ~(size_t)15) + ((thr + 15) & ~(size_t)15);
+    *masks_in_smem = other_bytes + base + mask_bytes + 64 <= (size_t)kSharedSmemBudget;
+    return base + (*masks_in_smem ? mask_bytes : 0);
 }
 
 // All threads: copy the index into shared memory at `smem` (16-byte aligned).  Visible after the
@@ -105,12 +105,11 @@ __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restri
     const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(g_index + PredIndexLayout::kHeader);
     PredIndexView v;
     v.num_bp = h->num_bp;
-    v.row_bytes = h->row_words * 4;
-    v.row_shift = h->row_shift;
+    v.row_words = h->row_words;
     v.direct = h->direct != 0;
     const uint32_t locator_bytes = v.direct ? (2u << h->w) : (uint32_t)kBuckets * 8;
     const uint32_t thr_bytes = v.direct ? 0u : v.num_bp * 4;
-    const uint32_t mask_bytes = (v.num_bp + 1) * v.row_bytes;
+    const uint32_t mask_bytes = (v.num_bp + 1) * v.row_words * 4;
     uint8_t* s_loc = smem;
     uint8_t* s_thr = s_loc + ((locator_bytes + 15) & ~15u);
     uint8_t* s_mask = s_thr + ((thr_bytes + 15) & ~15u);
@@ -126,31 +125,98 @@ __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restri
     if (masks_in_smem) {
         copy(s_mask, g_index + PredIndexLayout::kMasks, mask_bytes);
         v.masks = reinterpret_cast<const uint32_t*>(s_mask);
+        v.masks_saddr = smem_u32(s_mask);
     } else {
+        v.masks_saddr = 0;
         v.masks = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kMasks);
     }
     return v;
 }
 
-// byte offset of the mask row of a LEFT-aligned code t (garbage allowed in the low 32-W bits)
-template <int W>
-__device__ __forceinline__ uint32_t mask_row_offset(const PredIndexView& ix, uint32_t t)
-{
-    if constexpr (W <= kDirectMaxW) {
-        return static_cast<const uint16_t*>(ix.locator)[t >> (32 - W)] * ix.row_bytes;
-    } else {
-        const uint2 e = static_cast<const uint2*>(ix.locator)[t >> (32 - kBucketBits)];
-        // e.x = threshold of the bucket's first breakpoint (0xFFFFFFFF: none), e.y = first id | count << 16
-        uint32_t id = (e.y & 0xFFFFu) + (t > e.x ? 1u : 0u);
-        if (e.y >= (2u << 16)) {  // rare: several breakpoints inside one bucket
-            const uint32_t first = e.y & 0xFFFFu, cnt = e.y >> 16;
-            for (uint32_t i = 1; i < cnt; i++) id += (t > ix.thr[first + i]) ? 1u : 0u;
+// ---- interval ids of the 32 codes of a block ---------------------------------------------------
+//
+// id(code) = number of breakpoints <= code, from the LEFT-aligned code t (garbage allowed in the
+// low 32-W bits).  Branch-free for all 32 codes so that the 32 locator loads overlap; buckets that
+// hold two or more breakpoints are rare (K = 64: ~0.05 % of the codes of a uniform column) and are
+// patched up afterwards, once per block, in a path that is normally never taken.
+template <int W, int J>
+struct BlockIds {
+    static __device__ __forceinline__ void fast(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&id)[32],
+                                                uint32_t& flags)
+    {
+        const uint32_t t = left_aligned_code<W, J>(x);
+        if constexpr (W <= kDirectMaxW) {
+            id[J] = static_cast<const uint16_t*>(ix.locator)[t >> (32 - W)];
+        } else {
+            // e.x = threshold of the bucket's first breakpoint (0xFFFFFFFF: none), e.y = first id | count << 16
+            const uint2 e = static_cast<const uint2*>(ix.locator)[t >> (32 - kBucketBits)];
+            id[J] = (e.y & 0xFFFFu) + (t > e.x ? 1u : 0u);
+            flags |= e.y;
         }
-        return id * ix.row_bytes;
+        BlockIds<W, J + 1>::fast(x, ix, id, flags);
+    }
+    static __device__ __forceinline__ void slow(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&id)[32])
+    {
+        if constexpr (W > kDirectMaxW) {
+            const uint32_t t = left_aligned_code<W, J>(x);
+            const uint2 e = static_cast<const uint2*>(ix.locator)[t >> (32 - kBucketBits)];
+            const uint32_t first = e.y & 0xFFFFu, cnt = e.y >> 16;
+            uint32_t v = first;
+            for (uint32_t i = 0; i < cnt; i++) v += (t > ix.thr[first + i]) ? 1u : 0u;
+            id[J] = v;
+        }
+        BlockIds<W, J + 1>::slow(x, ix, id);
+    }
+};
+template <int W>
+struct BlockIds<W, 32> {
+    static __device__ __forceinline__ void fast(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32], uint32_t&) {}
+    static __device__ __forceinline__ void slow(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32]) {}
+};
+
+template <int W>
+__device__ __forceinline__ void block_ids(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&id)[32])
+{
+    uint32_t flags = 0;
+    BlockIds<W, 0>::fast(x, ix, id, flags);
+    if (flags >= (2u << 16)) BlockIds<W, 0>::slow(x, ix, id);  // some bucket holds >= 2 breakpoints
+}
+
+// word c of the mask row of interval `id`; kSmem selects shared-memory addressing (LDS) over the
+// generic path used when the table is too large for shared memory (K > 128 or so)
+template <bool kSmem>
+__device__ __forceinline__ uint32_t mask_word(const PredIndexView& ix, uint32_t id, int c)
+{
+    const uint32_t word = id * ix.row_words + (uint32_t)c;
+    if constexpr (kSmem) {
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ix.masks_saddr + word * 4));
+        return v;
+    } else {
+        return __ldg(ix.masks + word);
     }
 }
 
 // ---- 32 x 32 bit-matrix transpose in registers ------------------------------------------------------
+
+// (a & m) | (b & ~m) in ONE LOP3 (ptxas does not fuse the two-immediate form on its own)
+__device__ __forceinline__ uint32_t bit_select(uint32_t a, uint32_t b, uint32_t m)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+
+// one exchange stage on a register pair: swaps the high S-bit groups of `lo` with the low ones of `hi`
+template <int S>
+__device__ __forceinline__ void exchange_bits(uint32_t& lo, uint32_t& hi)
+{
+    constexpr uint32_t M = S == 4 ? 0x0F0F0F0Fu : (S == 2 ? 0x33333333u : 0x55555555u);
+    const uint32_t a = lo, b = hi;
+    lo = bit_select(a, b << S, M);
+    hi = bit_select(a >> S, b, M);
+}
+
 // in : a[j] bit k  = element (j, k)        (j = code index, k = predicate index)
 // out: a[k] bit j  = element (j, k)
 // Two byte-granular stages with PRMT, three bit-granular stages with shift + bit-select LOP3.
@@ -173,25 +239,13 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32])
 #pragma unroll
     for (int g = 0; g < 32; g += 8)
 #pragma unroll
-        for (int k = g; k < g + 4; k++) {  // 4 x 4 blocks
-            const uint32_t lo = a[k], hi = a[k + 4];
-            a[k] = (lo & 0x0F0F0F0Fu) | ((hi << 4) & 0xF0F0F0F0u);
-            a[k + 4] = ((lo >> 4) & 0x0F0F0F0Fu) | (hi & 0xF0F0F0F0u);
-        }
+        for (int k = g; k < g + 4; k++) exchange_bits<4>(a[k], a[k + 4]);
 #pragma unroll
     for (int g = 0; g < 32; g += 4)
 #pragma unroll
-        for (int k = g; k < g + 2; k++) {  // 2 x 2 blocks
-            const uint32_t lo = a[k], hi = a[k + 2];
-            a[k] = (lo & 0x33333333u) | ((hi << 2) & 0xCCCCCCCCu);
-            a[k + 2] = ((lo >> 2) & 0x33333333u) | (hi & 0xCCCCCCCCu);
-        }
+        for (int k = g; k < g + 2; k++) exchange_bits<2>(a[k], a[k + 2]);
 #pragma unroll
-    for (int k = 0; k < 32; k += 2) {  // 1 x 1
-        const uint32_t lo = a[k], hi = a[k + 1];
-        a[k] = (lo & 0x55555555u) | ((hi << 1) & 0xAAAAAAAAu);
-        a[k + 1] = ((lo >> 1) & 0x55555555u) | (hi & 0xAAAAAAAAu);
-    }
+    for (int k = 0; k < 32; k += 2) exchange_bits<1>(a[k], a[k + 1]);
 }
 
 }  // namespace sss

@@ -26,79 +26,86 @@ template <int W>
 struct SharedCfg {
     static constexpr int kBlocksPerTile = kThreads;  // one 32-code block per thread per tile
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
-    static constexpr int kStages = ring_stages(kTileBytes);
+    // compute-bound kernels: a shallow ring is enough and leaves shared memory for the mask table
+    static constexpr int kStages = kTileBytes >= 16 * 1024 ? 2 : 3;
     using Ring = TileRing<kTileBytes, kStages>;
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
 };
 
 constexpr int kCounterBytes = (kMaxBp + 1 + 3) / 4 * 16;  // up to 2K+1 uint32 interval counters, 16-byte multiple
 
-// mask-row offsets of the 32 codes of a block
-template <int W, int J>
-struct RowOffsets {
-    static __device__ __forceinline__ void run(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&off)[32])
-    {
-        off[J] = mask_row_offset<W>(ix, left_aligned_code<W, J>(x));
-        RowOffsets<W, J + 1>::run(x, ix, off);
-    }
-};
-template <int W>
-struct RowOffsets<W, 32> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32]) {}
-};
-
-template <int W>
+// kSmem: the mask table fits in shared memory (otherwise it is read through L1 from global memory)
+template <int W, bool kSmem>
 __global__ void __launch_bounds__(kThreads, 2)
 shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
-                   const uint8_t* __restrict__ g_index, int K, bool masks_in_smem, uint32_t* __restrict__ bitvecs,
-                   uint64_t stride_words, bool count_matches)
+                   const uint8_t* __restrict__ g_index, int K, uint32_t* __restrict__ bitvecs, uint64_t stride_words,
+                   bool count_matches)
 {
     using Cfg = SharedCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
     // per-CTA interval histogram (match counts are derived from it, see predindex.cuh)
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);
     for (int i = threadIdx.x; i < 2 * K + 1; i += kThreads) s_hist[i] = 0;
-    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kCounterBytes, masks_in_smem);
+    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kCounterBytes, kSmem);
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();  // contains the __syncthreads that publishes the index and the zeroed counters
 
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const int cols = (K + 31) >> 5;
-    const uint8_t* mask_base = reinterpret_cast<const uint8_t*>(ix.masks);
 
     uint32_t iter = 0;
     for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
         ring.wait(iter);
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
-        const bool active = gb < n_blocks;
-        uint32_t off[32];
-        if (active) {
-            uint32_t x[W];
+        if (gb < n_blocks) {
+            const bool last = tail_bits != 0 && gb == n_blocks - 1;  // the one ragged block of the column
+            uint32_t id[32];
+            {
+                uint32_t x[W];
 #pragma unroll
-            for (int k = 0; k < W; k++) x[k] = buf[threadIdx.x * W + k];
-            RowOffsets<W, 0>::run(x, ix, off);
-            if (count_matches) {
-                const uint32_t valid = (tail_bits != 0 && gb == n_blocks - 1) ? tail_bits : 32u;
-#pragma unroll
-                for (int j = 0; j < 32; j++)
-                    if ((uint32_t)j < valid) atomicAdd(&s_hist[off[j] >> ix.row_shift], 1u);
+                for (int k = 0; k < W; k++) x[k] = buf[threadIdx.x * W + k];
+                block_ids<W>(x, ix, id);
             }
-        } else {
+            if (count_matches) {
+                if (!last) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) off[j] = 0;
-        }
-        const uint32_t keep = (active && tail_bits != 0 && gb == n_blocks - 1) ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
-        for (int c = 0; c < cols; c++) {
-            uint32_t m[32];
+                    for (int j = 0; j < 32; j++) atomicAdd(&s_hist[id[j]], 1u);
+                } else {
+                    for (uint32_t j = 0; j < tail_bits; j++) {
+                        uint32_t v = 0;
 #pragma unroll
-            for (int j = 0; j < 32; j++) m[j] = *reinterpret_cast<const uint32_t*>(mask_base + off[j] + 4 * c);
-            transpose32(m);  // m[k'] bit j = predicate 32c+k' on code j
-            const int kk = K - 32 * c;  // predicates in this column (>= 32: full)
+                        for (int q = 0; q < 32; q++) v = (q == (int)j) ? id[q] : v;
+                        atomicAdd(&s_hist[v], 1u);
+                    }
+                }
+            }
+            uint32_t* p = bitvecs + gb;  // this block's word of predicate 0; += stride_words per predicate
+            for (int c = 0; c < cols; c++) {
+                uint32_t m[32];
 #pragma unroll
-            for (int k = 0; k < 32; k++) {
-                if (k < kk && active) st_stream_u32(bitvecs + (uint64_t)(32 * c + k) * stride_words + gb, m[k] & keep);
+                for (int j = 0; j < 32; j++) m[j] = mask_word<kSmem>(ix, id[j], c);
+                transpose32(m);  // m[k'] bit j = predicate 32c+k' on code j
+                if (last) {
+                    const uint32_t keep = (1u << tail_bits) - 1u;
+#pragma unroll
+                    for (int k = 0; k < 32; k++) m[k] &= keep;
+                }
+                const int kk = K - 32 * c;  // predicates in this column
+                if (kk >= 32) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        st_stream_u32(p, m[k]);
+                        p += stride_words;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        if (k < kk) st_stream_u32(p, m[k]);
+                        p += stride_words;
+                    }
+                }
             }
         }
         ring.release(iter, tile);
@@ -112,17 +119,16 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
     }
 }
 
-template <int W>
-static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K,
-                            uint32_t* bitvecs, uint64_t stride_words, bool count_matches, cudaStream_t stream)
+template <int W, bool kSmem>
+static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, const void* index, int K,
+                             uint32_t* bitvecs, uint64_t stride_words, bool count_matches, size_t smem,
+                             cudaStream_t stream)
 {
     using Cfg = SharedCfg<W>;
-    bool masks_in_smem = false;
-    const size_t smem = Cfg::kRingBytes + kCounterBytes + pred_index_smem_bytes(K, W, &masks_in_smem) + 64;
     static size_t configured[64] = {};
     if (configured[dev.ordinal & 63] < smem) {
-        cudaError_t e =
-            cudaFuncSetAttribute(shared_scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(shared_scan_kernel<W, kSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev.ordinal & 63] = smem;
     }
@@ -131,9 +137,21 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, c
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, static_cast<const uint8_t*>(index), K,
-                                                           masks_in_smem, bitvecs, stride_words, count_matches);
+    shared_scan_kernel<W, kSmem><<<grid, kThreads, smem, stream>>>(
+        packed, readable, n, static_cast<const uint8_t*>(index), K, bitvecs, stride_words, count_matches);
     return cudaGetLastError();
+}
+
+template <int W>
+static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K,
+                            uint32_t* bitvecs, uint64_t stride_words, bool count_matches, cudaStream_t stream)
+{
+    bool masks_in_smem = false;
+    const size_t other = SharedCfg<W>::kRingBytes + kCounterBytes;
+    const size_t smem = other + pred_index_smem_bytes(K, W, other, &masks_in_smem) + 64;
+    if (masks_in_smem)
+        return launch_ws<W, true>(dev, packed, n, index, K, bitvecs, stride_words, count_matches, smem, stream);
+    return launch_ws<W, false>(dev, packed, n, index, K, bitvecs, stride_words, count_matches, smem, stream);
 }
 
 using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, uint32_t*, uint64_t, bool,
