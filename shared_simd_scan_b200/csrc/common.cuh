@@ -117,11 +117,12 @@ template <int kTileBytes, int kStages, int kPadBytes = 16>
 struct TileRing {
     static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
     static constexpr int kStageBytes = kTileBytes + kPadBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kStages * 8;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStages * 8 + kStages * 4 + 16;
     static_assert(kStageBytes % 16 == 0, "stage base must stay 16-byte aligned");
 
     uint8_t* base;
     uint64_t* full;
+    uint32_t* released;   // per stage: warps that have finished reading it (release_warp protocol)
     const uint8_t* src;
     uint64_t src_bytes;   // readable bytes of the packed column, rounded up to 16
     uint64_t num_tiles;
@@ -129,7 +130,7 @@ struct TileRing {
 
     __device__ __forceinline__ TileRing(uint8_t* smem, const void* packed, uint64_t readable_bytes16)
         : base(smem), full(reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes)),
-          src(static_cast<const uint8_t*>(packed)), src_bytes(readable_bytes16),
+          released(reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + kStages * 8)), src(static_cast<const uint8_t*>(packed)), src_bytes(readable_bytes16),
           num_tiles((readable_bytes16 + kTileBytes - 1) / kTileBytes), policy(0)
     {
     }
@@ -153,7 +154,10 @@ struct TileRing {
     __device__ __forceinline__ void start()
     {
         if (threadIdx.x == 0) {
-            for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
+            for (int s = 0; s < kStages; s++) {
+                mbar_init(&full[s], 1);
+                released[s] = 0;
+            }
             fence_mbar_init();
             policy = l2_policy_evict_first();
         }
@@ -167,6 +171,33 @@ struct TileRing {
     __device__ __forceinline__ void wait(uint32_t iter)
     {
         mbar_wait(&full[iter % kStages], (iter / kStages) & 1u);
+    }
+
+    // Barrier-free release for kernels that copy their part of the tile into registers first and
+    // compute afterwards: every warp calls this once it has READ its words of the stage (pass one of
+    // the loaded values as `dep` so the call cannot be scheduled above the loads).  The last of the
+    // CTA's warps to arrive refills the stage itself; nobody waits for anybody.
+    __device__ __forceinline__ void release_warp(uint32_t iter, uint64_t tile, uint32_t dep)
+    {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            const int stage = iter % kStages;
+            uint32_t old;
+            // `dep` is an unused operand: it only forces the loads that produced it to have completed
+            asm volatile("atom.shared.add.u32 %0, [%1], %2;  // after %3"
+                         : "=r"(old)
+                         : "r"(smem_u32(&released[stage])), "r"(1u), "r"(dep)
+                         : "memory");
+            if (old == (blockDim.x >> 5) - 1) {
+                released[stage] = 0;  // next touched only after the refilled tile has landed
+                const uint64_t next = tile + (uint64_t)kStages * gridDim.x;
+                if (next < num_tiles) {
+                    fence_proxy_async();
+                    if (policy == 0) policy = l2_policy_evict_first();
+                    issue(next, stage);
+                }
+            }
+        }
     }
 
     // all threads, after the tile of iteration `iter` has been consumed

@@ -24,9 +24,17 @@
 
 namespace sss {
 
+// Threads per CTA of the index-driven kernels.  They are latency-bound (dependent shared-memory
+// lookups), so more resident warps help: 2 CTAs x 320 threads = 20 warps/SM within the register file
+// at <= 102 registers per thread.
+#ifndef SSS_SHARED_THREADS
+#define SSS_SHARED_THREADS 256
+#endif
+constexpr int kSThreads = SSS_SHARED_THREADS;
+
 template <int W>
 struct LinearCfg {
-    static constexpr int kBlocksPerTile = kThreads;
+    static constexpr int kBlocksPerTile = kSThreads;
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
     // compute-bound kernels: a shallow ring is enough and leaves shared memory for the mask table
     static constexpr int kStages = kTileBytes >= 16 * 1024 ? 2 : 3;
@@ -69,14 +77,14 @@ __device__ __forceinline__ void exchange_linear(uint32_t (&a)[32])
 }
 
 template <int W, bool kSmem>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kSThreads, 2)
 shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                           const uint8_t* __restrict__ g_index, int K, uint8_t* __restrict__ out, bool count_matches)
 {
     using Cfg = LinearCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);  // per-CTA interval histogram
-    for (int i = threadIdx.x; i < 2 * K + 1; i += kThreads) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < 2 * K + 1; i += kSThreads) s_hist[i] = 0;
     const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kLinCounterBytes, kSmem);
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();
@@ -93,15 +101,18 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
         ring.wait(iter);
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
-        if (gb < n_blocks) {
+        const bool active = gb < n_blocks;
+        uint32_t x[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) x[k] = active ? buf[threadIdx.x * W + k] : 0u;
+        uint32_t loaded = 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) loaded |= x[k];
+        ring.release_warp(iter, tile, loaded);  // the stage is free once every warp has copied its words
+        if (active) {
             const bool last = tail_bits != 0 && gb == n_blocks - 1;  // the one ragged block of the column
             uint32_t id[32];
-            {
-                uint32_t x[W];
-#pragma unroll
-                for (int k = 0; k < W; k++) x[k] = buf[threadIdx.x * W + k];
-                block_ids<W>(x, ix, id);
-            }
+            block_ids<W>(x, ix, id);
             if (count_matches) {
                 if (!last) {
 #pragma unroll
@@ -152,13 +163,12 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
                 }
             }
         }
-        ring.release(iter, tile);
     }
     __syncthreads();
     if (count_matches) {
         unsigned long long* g_hist =
             reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(g_index) + PredIndexLayout::kHist);
-        for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += kThreads)
+        for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += kSThreads)
             if (s_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)s_hist[i]);
     }
 }
@@ -180,7 +190,7 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_linear_kernel<W, kSmem><<<grid, kThreads, smem, stream>>>(
+    shared_scan_linear_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(
         packed, readable, n, static_cast<const uint8_t*>(index), K, out, count_matches);
     return cudaGetLastError();
 }

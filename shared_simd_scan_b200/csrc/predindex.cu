@@ -149,17 +149,16 @@ build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restr
         uint16_t* lut = reinterpret_cast<uint16_t*>(index + PredIndexLayout::kLocator);
         for (uint32_t v = tid; v < (1u << w); v += kBuildThreads) lut[v] = (uint16_t)count_le(bp, M, v);
     } else {
-        uint2* bucket = reinterpret_cast<uint2*>(index + PredIndexLayout::kLocator);
+        uint32_t* bucket = reinterpret_cast<uint32_t*>(index + PredIndexLayout::kLocator);
         const int shift = w - kBucketBits;
         for (uint32_t b = tid; b < (uint32_t)kBuckets; b += kBuildThreads) {
             const unsigned long long start = (unsigned long long)b << shift;
             const unsigned long long end = start + (1ull << shift) - 1;
-            const uint32_t first = start == 0 ? 0u : count_le(bp, M, start - 1);
-            const uint32_t cnt = count_le(bp, M, end) - first;
-            uint2 e;
-            e.x = cnt ? ((bp[first] << (32 - w)) - 1u) : 0xFFFFFFFFu;
-            e.y = first | (cnt << 16);
-            bucket[b] = e;
+            const uint32_t base = count_le(bp, M, start);        // breakpoints <= bucket start: in the id already
+            const uint32_t inner = count_le(bp, M, end) - base;  // start < breakpoint <= end
+            // threshold on the bits below the bucket bits of the LEFT-aligned code
+            const uint32_t thr = inner ? (((bp[base] << (32 - w)) & kThrMask) - 1u) : kThrMask;
+            bucket[b] = (base << (kThrBits + 1)) | (inner >= 2 ? kSeveralBit : 0u) | thr;
         }
     }
 }

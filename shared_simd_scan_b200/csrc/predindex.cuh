@@ -13,9 +13,10 @@
 //   interval id  id(v) = #{ i : bp[i] <= v }                      in [0, M]
 //   mask rows    mask[id][k] = 1  iff  lo_k <= start(id) <= hi_k   ceil(K/32) words per row
 //   locator      W <= 13 : lut[v] = id(v) * row_bytes             (direct, 2 bytes per code value)
-//                W  > 13 : 4096 buckets on the top 12 bits of the code: (first row offset, count of
-//                          breakpoints inside, left-aligned first breakpoint - 1); a bucket with at
-//                          most one breakpoint resolves with one compare, more fall to a short loop
+//                W  > 13 : 8192 buckets on the top 13 bits of the code, ONE 32-bit word each:
+//                          [id at bucket start : 12][several breakpoints inside : 1][threshold : 19];
+//                          a bucket with at most one inner breakpoint resolves with one compare of the
+//                          code's remaining bits against the threshold, the rare others re-search
 //
 // Built on the device by one CTA (bitonic sort of <= 2048 bounds, compaction, row/bucket fill) on
 // the caller's stream -- no host round trip.  The scan kernels copy it to shared memory at start.
@@ -28,7 +29,7 @@ namespace sss {
 constexpr int kMaxK = 1024;            // == SSS_MAX_PREDICATES
 constexpr int kMaxBp = 2 * kMaxK;      // breakpoints
 constexpr int kDirectMaxW = 13;        // direct locator up to 2^13 code values
-constexpr int kBucketBits = 12;
+constexpr int kBucketBits = 13;
 constexpr int kBuckets = 1 << kBucketBits;
 constexpr int kSharedSmemBudget = 112 * 1024;  // per CTA, two CTAs per SM: the mask table lives in shared
                                                // memory whenever ring + counters + index fit in this
@@ -58,8 +59,8 @@ inline uint32_t pred_row_stride_words(int K) { return (((uint32_t)K + 31) / 32) 
 struct PredIndexLayout {
     static constexpr size_t kHeader = 0;                                   // PredIndexHeader (32 B)
     static constexpr size_t kThr = 32;                                     // uint32 thr[kMaxBp]: (bp << (32-W)) - 1
-    static constexpr size_t kLocator = kThr + (size_t)kMaxBp * 4;          // lut16[2^W] or uint2 bucket[4096]
-    static constexpr size_t kLocatorBytes = (size_t)kBuckets * 8;          // 32 KB >= 2^13 * 2
+    static constexpr size_t kLocator = kThr + (size_t)kMaxBp * 4;          // lut16[2^W] or uint32 bucket[4096]
+    static constexpr size_t kLocatorBytes = (size_t)kBuckets * 4;          // 16 KB == 2^13 * 2
     static constexpr size_t kMasks = kLocator + kLocatorBytes;             // uint32 mask[(M+1)][row_words]
     static constexpr size_t kMasksBytes = ((size_t)(kMaxBp + 1) * (kMaxK / 32 + 1) * 4 + 255) / 256 * 256;
     static constexpr size_t kHist = kMasks + kMasksBytes + 256;            // unsigned long long hist[kMaxBp + 1]
@@ -90,7 +91,7 @@ inline size_t pred_index_smem_bytes(int K, int w, size_t other_bytes, bool* mask
     const size_t stride = pred_row_stride_words(K);
     const size_t max_rows = (w >= 31) ? (size_t)(2 * K + 1) : std::min<size_t>((size_t)2 * K + 1, (size_t)1 << w);
     const size_t mask_bytes = (max_rows * stride * 4 + 15) & ~(size_t)15;
-    const size_t locator = (w <= kDirectMaxW) ? ((size_t)2 << w) : (size_t)kBuckets * 8;
+    const size_t locator = (w <= kDirectMaxW) ? ((size_t)2 << w) : (size_t)kBuckets * 4;
     const size_t thr = (w <= kDirectMaxW) ? 0 : std::min<size_t>(2 * (size_t)K, kMaxBp) * 4;
     const size_t base = ((locator + 15) & ~(size_t)15) + ((thr + 15) & ~(size_t)15);
     *masks_in_smem = other_bytes + base + mask_bytes + 64 <= (size_t)kSharedSmemBudget;
@@ -107,7 +108,7 @@ __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restri
     v.num_bp = h->num_bp;
     v.row_words = h->row_words;
     v.direct = h->direct != 0;
-    const uint32_t locator_bytes = v.direct ? (2u << h->w) : (uint32_t)kBuckets * 8;
+    const uint32_t locator_bytes = v.direct ? (2u << h->w) : (uint32_t)kBuckets * 4;
     const uint32_t thr_bytes = v.direct ? 0u : v.num_bp * 4;
     const uint32_t mask_bytes = (v.num_bp + 1) * v.row_words * 4;
     uint8_t* s_loc = smem;
@@ -136,9 +137,18 @@ __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restri
 // ---- interval ids of the 32 codes of a block ---------------------------------------------------
 //
 // id(code) = number of breakpoints <= code, from the LEFT-aligned code t (garbage allowed in the
-// low 32-W bits).  Branch-free for all 32 codes so that the 32 locator loads overlap; buckets that
-// hold two or more breakpoints are rare (K = 64: ~0.05 % of the codes of a uniform column) and are
-// patched up afterwards, once per block, in a path that is normally never taken.
+// low 32-W bits).  Branch-free for all 32 codes so that the 32 locator loads overlap.
+//
+// Bucket word e = id_at_bucket_start << 20 | several << 19 | thr19.  The bucket fixes the top 13
+// bits of t, so only the remaining 19 decide:  t >= breakpoint  <=>  (t << 13) > (e << 13)  with
+// thr19 = (left-aligned breakpoint & 0x7FFFF) - 1, and thr19 = 0x7FFFF (never exceeded) for a bucket
+// without an inner breakpoint.  Buckets with two or more inner breakpoints (K = 64: ~0.01 % of the
+// codes of a uniform column) set `several`; the codes that fall into one are re-located by binary
+// search in a compact, rarely executed loop.
+constexpr int kThrBits = 32 - kBucketBits;           // 19
+constexpr uint32_t kThrMask = (1u << kThrBits) - 1;  // 0x7FFFF
+constexpr uint32_t kSeveralBit = 1u << kThrBits;
+
 template <int W, int J>
 struct BlockIds {
     static __device__ __forceinline__ void fast(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&id)[32],
@@ -148,38 +158,56 @@ struct BlockIds {
         if constexpr (W <= kDirectMaxW) {
             id[J] = static_cast<const uint16_t*>(ix.locator)[t >> (32 - W)];
         } else {
-            // e.x = threshold of the bucket's first breakpoint (0xFFFFFFFF: none), e.y = first id | count << 16
-            const uint2 e = static_cast<const uint2*>(ix.locator)[t >> (32 - kBucketBits)];
-            id[J] = (e.y & 0xFFFFu) + (t > e.x ? 1u : 0u);
-            flags |= e.y;
+            const uint32_t e = static_cast<const uint32_t*>(ix.locator)[t >> (32 - kBucketBits)];
+            id[J] = (e >> (kThrBits + 1)) + ((t << kBucketBits) > (e << kBucketBits) ? 1u : 0u);
+            flags |= e;
         }
         BlockIds<W, J + 1>::fast(x, ix, id, flags);
-    }
-    static __device__ __forceinline__ void slow(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&id)[32])
-    {
-        if constexpr (W > kDirectMaxW) {
-            const uint32_t t = left_aligned_code<W, J>(x);
-            const uint2 e = static_cast<const uint2*>(ix.locator)[t >> (32 - kBucketBits)];
-            const uint32_t first = e.y & 0xFFFFu, cnt = e.y >> 16;
-            uint32_t v = first;
-            for (uint32_t i = 0; i < cnt; i++) v += (t > ix.thr[first + i]) ? 1u : 0u;
-            id[J] = v;
-        }
-        BlockIds<W, J + 1>::slow(x, ix, id);
     }
 };
 template <int W>
 struct BlockIds<W, 32> {
     static __device__ __forceinline__ void fast(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32], uint32_t&) {}
-    static __device__ __forceinline__ void slow(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32]) {}
 };
+
+// rare path, kept small (one loop, runtime code index): returns the id of code j by binary search
+// over the thresholds if its bucket holds several breakpoints, else 0xFFFFFFFF (keep the fast id)
+template <int W>
+__device__ __noinline__ uint32_t relocate(const uint32_t* xs, int j, const uint32_t* locator, const uint32_t* thr,
+                                           uint32_t num_bp)
+{
+    const uint32_t bit = (uint32_t)j * W;
+    const uint32_t wi = bit >> 5;
+    const uint32_t v = __funnelshift_r(xs[wi], xs[wi + 1 < (uint32_t)W ? wi + 1 : wi], bit & 31) & code_mask(W);
+    const uint32_t t = v << (32 - W);  // left-aligned, zero-filled
+    if (!(locator[t >> (32 - kBucketBits)] & kSeveralBit)) return 0xFFFFFFFFu;
+    uint32_t lo = 0, hi = num_bp;  // number of thr[i] < t  (thr ascending)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (t > thr[mid]) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
 
 template <int W>
 __device__ __forceinline__ void block_ids(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&id)[32])
 {
     uint32_t flags = 0;
     BlockIds<W, 0>::fast(x, ix, id, flags);
-    if (flags >= (2u << 16)) BlockIds<W, 0>::slow(x, ix, id);  // some bucket holds >= 2 breakpoints
+    if constexpr (W > kDirectMaxW) {
+        if (flags & kSeveralBit) {  // some code of this block fell into a bucket with >= 2 inner breakpoints
+            uint32_t xs[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) xs[k] = x[k];
+            for (int j = 0; j < 32; j++) {
+                const uint32_t v = relocate<W>(xs, j, static_cast<const uint32_t*>(ix.locator), ix.thr, ix.num_bp);
+                if (v != 0xFFFFFFFFu) {
+#pragma unroll
+                    for (int q = 0; q < 32; q++) id[q] = (q == j) ? v : id[q];
+                }
+            }
+        }
+    }
 }
 
 // word c of the mask row of interval `id`; kSmem selects shared-memory addressing (LDS) over the
@@ -187,7 +215,11 @@ __device__ __forceinline__ void block_ids(const uint32_t (&x)[W], const PredInde
 template <bool kSmem>
 __device__ __forceinline__ uint32_t mask_word(const PredIndexView& ix, uint32_t id, int c)
 {
+#ifdef SSS_EXPERIMENT_NOCONFLICT_MASK
+    const uint32_t word = ((id & 3) * 32 + (threadIdx.x & 31)) * ix.row_words + (uint32_t)c;
+#else
     const uint32_t word = id * ix.row_words + (uint32_t)c;
+#endif
     if constexpr (kSmem) {
         uint32_t v;
         asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ix.masks_saddr + word * 4));

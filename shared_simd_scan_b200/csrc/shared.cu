@@ -22,9 +22,17 @@
 
 namespace sss {
 
+// Threads per CTA of the index-driven kernels.  They are latency-bound (dependent shared-memory
+// lookups), so more resident warps help: 2 CTAs x 320 threads = 20 warps/SM within the register file
+// at <= 102 registers per thread.
+#ifndef SSS_SHARED_THREADS
+#define SSS_SHARED_THREADS 256
+#endif
+constexpr int kSThreads = SSS_SHARED_THREADS;
+
 template <int W>
 struct SharedCfg {
-    static constexpr int kBlocksPerTile = kThreads;  // one 32-code block per thread per tile
+    static constexpr int kBlocksPerTile = kSThreads;  // one 32-code block per thread per tile
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
     // compute-bound kernels: a shallow ring is enough and leaves shared memory for the mask table
     static constexpr int kStages = kTileBytes >= 16 * 1024 ? 2 : 3;
@@ -36,7 +44,7 @@ constexpr int kCounterBytes = (kMaxBp + 1 + 3) / 4 * 16;  // up to 2K+1 uint32 i
 
 // kSmem: the mask table fits in shared memory (otherwise it is read through L1 from global memory)
 template <int W, bool kSmem>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kSThreads, 2)
 shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                    const uint8_t* __restrict__ g_index, int K, uint32_t* __restrict__ bitvecs, uint64_t stride_words,
                    bool count_matches)
@@ -45,7 +53,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
     extern __shared__ __align__(128) uint8_t smem[];
     // per-CTA interval histogram (match counts are derived from it, see predindex.cuh)
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);
-    for (int i = threadIdx.x; i < 2 * K + 1; i += kThreads) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < 2 * K + 1; i += kSThreads) s_hist[i] = 0;
     const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kCounterBytes, kSmem);
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();  // contains the __syncthreads that publishes the index and the zeroed counters
@@ -59,15 +67,18 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
         ring.wait(iter);
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
-        if (gb < n_blocks) {
+        const bool active = gb < n_blocks;
+        uint32_t x[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) x[k] = active ? buf[threadIdx.x * W + k] : 0u;
+        uint32_t loaded = 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) loaded |= x[k];
+        ring.release_warp(iter, tile, loaded);  // the stage is free once every warp has copied its words
+        if (active) {
             const bool last = tail_bits != 0 && gb == n_blocks - 1;  // the one ragged block of the column
             uint32_t id[32];
-            {
-                uint32_t x[W];
-#pragma unroll
-                for (int k = 0; k < W; k++) x[k] = buf[threadIdx.x * W + k];
-                block_ids<W>(x, ix, id);
-            }
+            block_ids<W>(x, ix, id);
             if (count_matches) {
                 if (!last) {
 #pragma unroll
@@ -96,7 +107,11 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
                 if (kk >= 32) {
 #pragma unroll
                     for (int k = 0; k < 32; k++) {
+#ifndef SSS_EXPERIMENT_NO_STORE
                         st_stream_u32(p, m[k]);
+#else
+                        if (m[k] == 0x12345678u && stride_words == 1) st_stream_u32(p, m[k]);
+#endif
                         p += stride_words;
                     }
                 } else {
@@ -108,13 +123,12 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
                 }
             }
         }
-        ring.release(iter, tile);
     }
     __syncthreads();
     if (count_matches) {
         unsigned long long* g_hist =
             reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(g_index) + PredIndexLayout::kHist);
-        for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += kThreads)
+        for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += kSThreads)
             if (s_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)s_hist[i]);
     }
 }
@@ -137,7 +151,7 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_kernel<W, kSmem><<<grid, kThreads, smem, stream>>>(
+    shared_scan_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(
         packed, readable, n, static_cast<const uint8_t*>(index), K, bitvecs, stride_words, count_matches);
     return cudaGetLastError();
 }

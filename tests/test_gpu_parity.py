@@ -259,3 +259,30 @@ def test_range_shards_concatenate_to_the_whole(sss):
     assert (np.concatenate(pieces)[: (n + 7) // 8] == host(whole)[: (n + 7) // 8]).all()
     pos, num = sss.positions(whole, n)
     assert (np.concatenate(allpos) == host(pos)[: int(num.item())]).all()
+
+
+@pytest.mark.parametrize("w", [14, 17, 25, 32])
+def test_shared_scan_clustered_bounds_and_codes(sss, w):
+    """Many predicates and most codes inside a handful of locator buckets: exercises the path for
+    buckets that hold several breakpoints (rare on uniform data, so forced here)."""
+    n, K = 20_011, 96
+    rng = np.random.default_rng(w)
+    m = (1 << w) - 1
+    center = m // 3
+    codes = (center + rng.integers(-300, 300, size=n)).astype(np.int64)
+    codes[::7] = rng.integers(0, m + 1, size=len(codes[::7]))       # some far-away codes too
+    codes = np.clip(codes, 0, m).astype(np.uint32)
+    packed = B.pack(codes, w)
+    lo = np.clip(center + rng.integers(-320, 320, size=K), 0, m).astype(np.uint64)
+    hi = np.minimum(lo + rng.integers(0, 40, size=K).astype(np.uint64), m)
+    lo[5], hi[5] = 0, m          # everything
+    lo[6], hi[6] = m, m          # the top code only
+    exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
+    bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi)
+    nb = (n + 7) // 8
+    assert (host(bv)[:, :nb] == exp).all()
+    assert (host(cnt).astype(np.uint64) == ecnt).all()
+    lexp, lcnt = B.shared_scan_linear(packed, n, w, lo, hi, granule=1)
+    lin, cnt2 = sss.shared_scan_linear(dev(packed), n, w, lo, hi)
+    assert (host(lin)[:nb] == lexp).all()
+    assert (host(cnt2).astype(np.uint64) == lcnt).all()

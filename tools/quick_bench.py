@@ -71,9 +71,15 @@ def main():
                     hi = torch.clamp(lo + torch.randint(0, max(2, (m + 1) // K * 2), (K,), generator=g), max=m)
                     lo_d, hi_d = lo.to(torch.int32).cuda(), hi.to(torch.int32).cuda()
                     cnt = torch.empty(K, dtype=torch.int64, device="cuda")
+                    nocount = bool(os.environ.get("SSS_QB_NOCOUNT"))
                     if op == "shared":
                         out = torch.empty((K, api.bitvec_bytes(n2) // 16 * 16 + 16), dtype=torch.uint8, device="cuda")
-                        f = lambda: api.shared_scan(packed, n2, w, lo_d, hi_d, out=out, counts=cnt)  # noqa: E731
+                        if nocount:
+                            from shared_simd_scan_b200._lib import lib, check
+                            ctx = api.Context.current()
+                            f = lambda: check(lib().sss_shared_scan(ctx.handle, packed.data_ptr(), n2, w, lo_d.data_ptr(), hi_d.data_ptr(), K, out.data_ptr(), out.stride(0), None, torch.cuda.current_stream().cuda_stream), "x")  # noqa: E731
+                        else:
+                            f = lambda: api.shared_scan(packed, n2, w, lo_d, hi_d, out=out, counts=cnt)  # noqa: E731
                     else:
                         out = torch.empty((4 * ((n2 + 31) // 32), K), dtype=torch.uint8, device="cuda")
                         f = lambda: api.shared_scan_linear(packed, n2, w, lo_d, hi_d, out=out, counts=cnt)  # noqa: E731
