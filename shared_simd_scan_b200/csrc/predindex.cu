@@ -128,6 +128,7 @@ build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restr
     for (uint32_t i = tid; i <= M; i += kBuildThreads) hist[i] = 0;
     uint32_t* thr = reinterpret_cast<uint32_t*>(index + PredIndexLayout::kThr);
     for (uint32_t i = tid; i < M; i += kBuildThreads) thr[i] = (bp[i] << (32 - w)) - 1u;
+    if (tid == 0) thr[M] = 0xFFFFFFFFu;  // sentinel: ends every forward walk
 
     // 4. mask rows
     uint32_t* masks = reinterpret_cast<uint32_t*>(index + PredIndexLayout::kMasks);

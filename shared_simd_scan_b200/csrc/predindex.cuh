@@ -59,7 +59,7 @@ inline uint32_t pred_row_stride_words(int K) { return (((uint32_t)K + 31) / 32) 
 struct PredIndexLayout {
     static constexpr size_t kHeader = 0;                                   // PredIndexHeader (32 B)
     static constexpr size_t kThr = 32;                                     // uint32 thr[kMaxBp]: (bp << (32-W)) - 1
-    static constexpr size_t kLocator = kThr + (size_t)kMaxBp * 4;          // lut16[2^W] or uint32 bucket[4096]
+    static constexpr size_t kLocator = kThr + (size_t)kMaxBp * 4 + 16;          // lut16[2^W] or uint32 bucket[4096]
     static constexpr size_t kLocatorBytes = (size_t)kBuckets * 4;          // 16 KB == 2^13 * 2
     static constexpr size_t kMasks = kLocator + kLocatorBytes;             // uint32 mask[(M+1)][row_words]
     static constexpr size_t kMasksBytes = ((size_t)(kMaxBp + 1) * (kMaxK / 32 + 1) * 4 + 255) / 256 * 256;
@@ -92,7 +92,7 @@ inline size_t pred_index_smem_bytes(int K, int w, size_t other_bytes, bool* mask
     const size_t max_rows = (w >= 31) ? (size_t)(2 * K + 1) : std::min<size_t>((size_t)2 * K + 1, (size_t)1 << w);
     const size_t mask_bytes = (max_rows * stride * 4 + 15) & ~(size_t)15;
     const size_t locator = (w <= kDirectMaxW) ? ((size_t)2 << w) : (size_t)kBuckets * 4;
-    const size_t thr = (w <= kDirectMaxW) ? 0 : std::min<size_t>(2 * (size_t)K, kMaxBp) * 4;
+    const size_t thr = (w <= kDirectMaxW) ? 0 : (std::min<size_t>(2 * (size_t)K, kMaxBp) + 1) * 4;
     const size_t base = ((locator + 15) & ~(size_t)15) + ((thr + 15) & ~(size_t)15);
     *masks_in_smem = other_bytes + base + mask_bytes + 64 <= (size_t)kSharedSmemBudget;
     return base + (*masks_in_smem ? mask_bytes : 0);
@@ -109,7 +109,7 @@ __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restri
     v.row_words = h->row_words;
     v.direct = h->direct != 0;
     const uint32_t locator_bytes = v.direct ? (2u << h->w) : (uint32_t)kBuckets * 4;
-    const uint32_t thr_bytes = v.direct ? 0u : v.num_bp * 4;
+    const uint32_t thr_bytes = v.direct ? 0u : (v.num_bp + 1) * 4;  // + the 0xFFFFFFFF sentinel
     const uint32_t mask_bytes = (v.num_bp + 1) * v.row_words * 4;
     uint8_t* s_loc = smem;
     uint8_t* s_thr = s_loc + ((locator_bytes + 15) & ~15u);
@@ -143,8 +143,8 @@ __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restri
 // bits of t, so only the remaining 19 decide:  t >= breakpoint  <=>  (t << 13) > (e << 13)  with
 // thr19 = (left-aligned breakpoint & 0x7FFFF) - 1, and thr19 = 0x7FFFF (never exceeded) for a bucket
 // without an inner breakpoint.  Buckets with two or more inner breakpoints (K = 64: ~0.01 % of the
-// codes of a uniform column) set `several`; the codes that fall into one are re-located by binary
-// search in a compact, rarely executed loop.
+// codes of a uniform column; every equality predicate, whose breakpoints key and key+1 are
+// adjacent) set `several`; a block that met one patches the ids of exactly those codes (fix()).
 constexpr int kThrBits = 32 - kBucketBits;           // 19
 constexpr uint32_t kThrMask = (1u << kThrBits) - 1;  // 0x7FFFF
 constexpr uint32_t kSeveralBit = 1u << kThrBits;
@@ -164,50 +164,34 @@ struct BlockIds {
         }
         BlockIds<W, J + 1>::fast(x, ix, id, flags);
     }
+    // executed only by blocks that met a `several` bucket: the codes that fell into one walk the
+    // (sorted) thresholds from the bucket's first breakpoint; thr[num_bp] is a 0xFFFFFFFF sentinel
+    static __device__ __forceinline__ void fix(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&id)[32])
+    {
+        if constexpr (W > kDirectMaxW) {
+            const uint32_t t = left_aligned_code<W, J>(x);
+            const uint32_t e = static_cast<const uint32_t*>(ix.locator)[t >> (32 - kBucketBits)];
+            if (e & kSeveralBit) {
+                uint32_t i = e >> (kThrBits + 1);
+                while (t > ix.thr[i]) i++;
+                id[J] = i;
+            }
+        }
+        BlockIds<W, J + 1>::fix(x, ix, id);
+    }
 };
 template <int W>
 struct BlockIds<W, 32> {
     static __device__ __forceinline__ void fast(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32], uint32_t&) {}
+    static __device__ __forceinline__ void fix(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32]) {}
 };
-
-// rare path, kept small (one loop, runtime code index): returns the id of code j by binary search
-// over the thresholds if its bucket holds several breakpoints, else 0xFFFFFFFF (keep the fast id)
-template <int W>
-__device__ __noinline__ uint32_t relocate(const uint32_t* xs, int j, const uint32_t* locator, const uint32_t* thr,
-                                           uint32_t num_bp)
-{
-    const uint32_t bit = (uint32_t)j * W;
-    const uint32_t wi = bit >> 5;
-    const uint32_t v = __funnelshift_r(xs[wi], xs[wi + 1 < (uint32_t)W ? wi + 1 : wi], bit & 31) & code_mask(W);
-    const uint32_t t = v << (32 - W);  // left-aligned, zero-filled
-    if (!(locator[t >> (32 - kBucketBits)] & kSeveralBit)) return 0xFFFFFFFFu;
-    uint32_t lo = 0, hi = num_bp;  // number of thr[i] < t  (thr ascending)
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (t > thr[mid]) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
 
 template <int W>
 __device__ __forceinline__ void block_ids(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&id)[32])
 {
     uint32_t flags = 0;
     BlockIds<W, 0>::fast(x, ix, id, flags);
-    if constexpr (W > kDirectMaxW) {
-        if (flags & kSeveralBit) {  // some code of this block fell into a bucket with >= 2 inner breakpoints
-            uint32_t xs[W];
-#pragma unroll
-            for (int k = 0; k < W; k++) xs[k] = x[k];
-            for (int j = 0; j < 32; j++) {
-                const uint32_t v = relocate<W>(xs, j, static_cast<const uint32_t*>(ix.locator), ix.thr, ix.num_bp);
-                if (v != 0xFFFFFFFFu) {
-#pragma unroll
-                    for (int q = 0; q < 32; q++) id[q] = (q == j) ? v : id[q];
-                }
-            }
-        }
-    }
+    if (flags & kSeveralBit) BlockIds<W, 0>::fix(x, ix, id);
 }
 
 // word c of the mask row of interval `id`; kSmem selects shared-memory addressing (LDS) over the

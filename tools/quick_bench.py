@@ -69,6 +69,8 @@ def main():
                     g = torch.Generator().manual_seed(1)
                     lo = torch.randint(0, m + 1, (K,), generator=g)
                     hi = torch.clamp(lo + torch.randint(0, max(2, (m + 1) // K * 2), (K,), generator=g), max=m)
+                    if os.environ.get("SSS_QB_EQ"):
+                        hi = lo.clone()  # the reference's equality predicates
                     lo_d, hi_d = lo.to(torch.int32).cuda(), hi.to(torch.int32).cuda()
                     cnt = torch.empty(K, dtype=torch.int64, device="cuda")
                     nocount = bool(os.environ.get("SSS_QB_NOCOUNT"))
