@@ -76,6 +76,121 @@ __device__ __forceinline__ void exchange_linear(uint32_t (&a)[32])
     }
 }
 
+// 32 consecutive predicate bytes of one output row (8 words, already in row order); kk = predicates
+// that exist in this column (>= 32: all)
+__device__ __forceinline__ void store_row_piece(uint8_t* dst, const uint32_t (&ws)[8], int kk, bool vec16, bool vec4)
+{
+    if (vec16 && kk >= 32) {
+        __stcs(reinterpret_cast<uint4*>(dst), make_uint4(ws[0], ws[1], ws[2], ws[3]));
+        __stcs(reinterpret_cast<uint4*>(dst) + 1, make_uint4(ws[4], ws[5], ws[6], ws[7]));
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (4 * q + 4 <= kk && vec4) {
+                __stcs(reinterpret_cast<uint32_t*>(dst) + q, ws[q]);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (4 * q + b < kk) dst[4 * q + b] = (uint8_t)(ws[q] >> (8 * b));
+            }
+        }
+    }
+}
+
+// interval id of code `j` (runtime) of a block whose W words start at `blk` in shared memory
+template <int W>
+__device__ __forceinline__ uint32_t code_id_runtime(const uint32_t* blk, uint32_t j, const PredIndexView& ix)
+{
+    const uint32_t bit = j * W, wi = bit >> 5;
+    const uint32_t v = __funnelshift_r(blk[wi], blk[wi + 1 < (uint32_t)W ? wi + 1 : wi], bit & 31) & code_mask(W);
+    if constexpr (W <= kDirectMaxW) {
+        return static_cast<const uint16_t*>(ix.locator)[v];
+    } else {
+        const uint32_t t = v << (32 - W);
+        const uint32_t e = static_cast<const uint32_t*>(ix.locator)[t >> (32 - kBucketBits)];
+        uint32_t id = (e >> (kThrBits + 1)) + ((t << kBucketBits) > (e << kBucketBits) ? 1u : 0u);
+        if (e & kSeveralBit) {
+            uint32_t i = e >> (kThrBits + 1);
+            while (t > ix.thr[i]) i++;
+            id = i;
+        }
+        return id;
+    }
+}
+
+// ---- many predicates (more than 16 columns of 32): one warp per 32-code block, one lane per column ----
+//
+// With a row pitch of K >= 544 bytes the thread-per-block mapping above makes every warp store hit
+// 32 different rows.  Here lane j first locates code j of the block (one lookup per code, lane
+// parallel), the 32 interval ids are broadcast with shuffles, lane c then reads column c of the 32
+// mask rows (consecutive words of the same row across lanes: conflict-free), runs the exchange
+// network and owns bytes 32c..32c+31 of the block's four output rows -- so a warp writes each row as
+// one contiguous run of K bytes.
+template <int W, bool kSmem>
+__global__ void __launch_bounds__(kSThreads, 2)
+shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
+                               const uint8_t* __restrict__ g_index, int K, uint8_t* __restrict__ out,
+                               bool count_matches)
+{
+    using Cfg = LinearCfg<W>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);
+    for (int i = threadIdx.x; i < 2 * K + 1; i += kSThreads) s_hist[i] = 0;
+    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kLinCounterBytes, kSmem);
+    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    ring.start();
+
+    const uint64_t n_blocks = (n + 31) >> 5;
+    const uint32_t tail_bits = (uint32_t)(n & 31);
+    const int cols = (K + 31) >> 5;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool vec16 = (K & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const bool vec4 = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+    const int my_col = (int)lane < cols ? (int)lane : 0;   // lanes past the last column idle along
+    const int kk = K - 32 * (int)lane;                      // predicates in my column (<= 0: none)
+
+    uint32_t iter = 0;
+    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
+        ring.wait(iter);
+        const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
+        uint32_t dep = 0;
+        for (uint32_t b = 0; b < 32; b++) {
+            const uint32_t blk = warp * 32 + b;
+            const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + blk;
+            if (gb >= n_blocks) break;  // warp-uniform
+            const uint32_t valid = (tail_bits != 0 && gb == n_blocks - 1) ? tail_bits : 32u;
+            const uint32_t id = code_id_runtime<W>(buf + blk * W, lane, ix);
+            dep |= id;
+            if (count_matches && lane < valid) atomicAdd(&s_hist[id], 1u);
+            uint32_t m[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t idj = __shfl_sync(0xFFFFFFFFu, id, j);
+                m[j] = mask_word<kSmem>(ix, idj, my_col);
+                if ((uint32_t)j >= valid) m[j] = 0;  // codes past n contribute zero bits
+            }
+            exchange_linear(m);
+            if (kk > 0) {
+                uint8_t* row0 = out + gb * 4 * (uint64_t)K + 32 * lane;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t ws[8] = {m[8 * i + 0], m[8 * i + 4], m[8 * i + 1], m[8 * i + 5],
+                                            m[8 * i + 2], m[8 * i + 6], m[8 * i + 3], m[8 * i + 7]};
+                    store_row_piece(row0 + (uint64_t)i * K, ws, kk, vec16, vec4);
+                }
+            }
+        }
+        ring.release_warp(iter, tile, dep);
+    }
+    __syncthreads();
+    if (count_matches) {
+        unsigned long long* g_hist =
+            reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(g_index) + PredIndexLayout::kHist);
+        for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += kSThreads)
+            if (s_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)s_hist[i]);
+    }
+}
+
 template <int W, bool kSmem>
 __global__ void __launch_bounds__(kSThreads, 2)
 shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
@@ -142,24 +257,9 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
                 for (int i = 0; i < 4; i++) {
                     uint8_t* dst = row0 + (uint64_t)i * K + 32 * c;
                     // word q of the row = m[8i + 4*(q&1) + (q>>1)]
-                    const uint32_t w0 = m[8 * i + 0], w1 = m[8 * i + 4], w2 = m[8 * i + 1], w3 = m[8 * i + 5];
-                    const uint32_t w4 = m[8 * i + 2], w5 = m[8 * i + 6], w6 = m[8 * i + 3], w7 = m[8 * i + 7];
-                    if (vec16 && kk >= 32) {
-                        __stcs(reinterpret_cast<uint4*>(dst), make_uint4(w0, w1, w2, w3));
-                        __stcs(reinterpret_cast<uint4*>(dst) + 1, make_uint4(w4, w5, w6, w7));
-                    } else {
-                        const uint32_t ws[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            if (4 * q + 4 <= kk && vec4) {
-                                __stcs(reinterpret_cast<uint32_t*>(dst) + q, ws[q]);
-                            } else {
-#pragma unroll
-                                for (int b = 0; b < 4; b++)
-                                    if (4 * q + b < kk) dst[4 * q + b] = (uint8_t)(ws[q] >> (8 * b));
-                            }
-                        }
-                    }
+                    const uint32_t ws[8] = {m[8 * i + 0], m[8 * i + 4], m[8 * i + 1], m[8 * i + 5],
+                                            m[8 * i + 2], m[8 * i + 6], m[8 * i + 3], m[8 * i + 7]};
+                    store_row_piece(dst, ws, kk, vec16, vec4);
                 }
             }
         }
@@ -190,6 +290,18 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
+    if (K > 16 * 32) {
+        static size_t configured_wide[64] = {};
+        if (configured_wide[dev.ordinal & 63] < smem) {
+            cudaError_t e = cudaFuncSetAttribute(shared_scan_linear_wide_kernel<W, kSmem>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured_wide[dev.ordinal & 63] = smem;
+        }
+        shared_scan_linear_wide_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, count_matches);
+        return cudaGetLastError();
+    }
     shared_scan_linear_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(
         packed, readable, n, static_cast<const uint8_t*>(index), K, out, count_matches);
     return cudaGetLastError();

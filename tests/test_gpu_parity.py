@@ -286,3 +286,26 @@ def test_shared_scan_clustered_bounds_and_codes(sss, w):
     lin, cnt2 = sss.shared_scan_linear(dev(packed), n, w, lo, hi)
     assert (host(lin)[:nb] == lexp).all()
     assert (host(cnt2).astype(np.uint64) == lcnt).all()
+
+
+@pytest.mark.parametrize("w,K", [(9, 1024), (17, 1000), (12, 600), (32, 515), (5, 1024)])
+def test_many_predicates(sss, w, K):
+    """K > 512 takes the warp-per-block linear kernel and the histogram counts at full width."""
+    n = 9_973
+    rng = np.random.default_rng(w * 7 + K)
+    m = (1 << w) - 1
+    codes, packed = column(n, w, seed=600 + w)
+    lo = rng.integers(0, m + 1, size=K, dtype=np.uint64)
+    hi = np.minimum(lo + rng.integers(0, max(2, (m + 1) // 64), size=K, dtype=np.uint64), m)
+    hi[::5] = lo[::5]                       # equality predicates among them
+    lo[3], hi[3] = 9, 2                      # an empty one
+    lexp, lcnt = B.shared_scan_linear(packed, n, w, lo, hi, granule=1)
+    lin, cnt = sss.shared_scan_linear(dev(packed), n, w, lo, hi)
+    nb = (n + 7) // 8
+    assert (host(lin)[:nb] == lexp).all()
+    assert not host(lin)[nb:].any()
+    assert (host(cnt).astype(np.uint64) == lcnt).all()
+    exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
+    bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi)
+    assert (host(bv)[:, :nb] == exp).all()
+    assert (host(cnt).astype(np.uint64) == ecnt).all()
