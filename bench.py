@@ -44,6 +44,17 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def captured_traffic():
+    """DRAM bytes of the 32 scan launches of one step, from the committed ncu capture
+    (profiles/r01_scan_traffic.json; tools/scan_traffic.py + tools/summarise_traffic.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_scan_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["traffic_per_step"]), float(t["algorithmic_per_step"])
+    except Exception:
+        return None, None
+
+
 def predicate(w):
     """Range predicate of the sweep: [m/4, m/2] (about 25 % selectivity for w >= 3)."""
     m = (1 << w) - 1
@@ -303,7 +314,12 @@ def run_ours(args):
                 "steps": e2e_steps, "api": "sss_host_scan_range (pinned host buffers, 64 MiB chunks, 3 streams)"},
         "gpu_launches": args.steps * len(WIDTHS),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4),
+                     "traffic": captured_traffic()[0] if args.logn == 30 else None,
+                     "algorithmic_bytes": total_bytes,
+                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 32 launches of "
+                                       "one step at 2^30 codes (profiles/r01_scan_traffic.json)",
+                     "peak_source": peak_src,
                      "kernel": "sss::scan_range_kernel<W>, aggregated over the 32 launches of a step "
                                "(bytes = n*(w/8+1/8) per launch; per-launch numbers in per_width)",
                      "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},

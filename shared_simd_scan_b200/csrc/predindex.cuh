@@ -199,11 +199,7 @@ __device__ __forceinline__ void block_ids(const uint32_t (&x)[W], const PredInde
 template <bool kSmem>
 __device__ __forceinline__ uint32_t mask_word(const PredIndexView& ix, uint32_t id, int c)
 {
-#ifdef SSS_EXPERIMENT_NOCONFLICT_MASK
-    const uint32_t word = ((id & 3) * 32 + (threadIdx.x & 31)) * ix.row_words + (uint32_t)c;
-#else
     const uint32_t word = id * ix.row_words + (uint32_t)c;
-#endif
     if constexpr (kSmem) {
         uint32_t v;
         asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ix.masks_saddr + word * 4));

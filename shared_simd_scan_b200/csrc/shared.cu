@@ -107,11 +107,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
                 if (kk >= 32) {
 #pragma unroll
                     for (int k = 0; k < 32; k++) {
-#ifndef SSS_EXPERIMENT_NO_STORE
                         st_stream_u32(p, m[k]);
-#else
-                        if (m[k] == 0x12345678u && stride_words == 1) st_stream_u32(p, m[k]);
-#endif
                         p += stride_words;
                     }
                 } else {
