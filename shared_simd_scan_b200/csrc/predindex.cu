@@ -3,7 +3,7 @@
 //   1. every valid predicate contributes the breakpoints lo (if > 0) and hi+1 (if <= 2^W - 1)
 //   2. bitonic sort of the (<= 2048) breakpoints in shared memory, 64-bit keys (2^32 = "none")
 //   3. compaction of the distinct values (block prefix sum)
-//   4. mask rows: row i, predicate k  <-  lo_k <= start_i <= hi_k
+//   4. mask rows: row i, predicate k  <-  lo_k <= start_i <= hi_k   (fill_masks_kernel, many CTAs)
 //   5. locator: direct lut (W <= 13) or 4096 buckets on the top 12 bits
 #include <algorithm>
 
@@ -31,7 +31,6 @@ build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restr
 {
     __shared__ unsigned long long keys[kMaxBp];
     __shared__ uint32_t bp[kMaxBp];
-    __shared__ uint32_t s_lo[kMaxK], s_hi[kMaxK];  // clamped bounds; lo > hi marks an empty predicate
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t s_M;
 
@@ -41,21 +40,15 @@ build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restr
     // 1. bounds -> candidate breakpoints
     for (uint32_t k = tid; k < (uint32_t)kMaxK; k += kBuildThreads) {
         unsigned long long b0 = kNone, b1 = kNone;
-        uint32_t l = 1, h = 0;
         if (k < (uint32_t)K) {
-            l = lo[k];
-            h = hi[k];
-            if (l <= h && l <= maxv) {
+            const uint32_t l = lo[k];
+            uint32_t h = hi[k];
+            if (l <= h && l <= maxv) {  // valid predicate (hi clamps to the domain)
                 if (h > maxv) h = maxv;
                 if (l > 0) b0 = l;
                 if (h < maxv) b1 = (unsigned long long)h + 1;
-            } else {
-                l = 1;
-                h = 0;
             }
         }
-        s_lo[k] = l;
-        s_hi[k] = h;
         keys[2 * k] = b0;
         keys[2 * k + 1] = b1;
     }
@@ -130,20 +123,7 @@ build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restr
     for (uint32_t i = tid; i < M; i += kBuildThreads) thr[i] = (bp[i] << (32 - w)) - 1u;
     if (tid == 0) thr[M] = 0xFFFFFFFFu;  // sentinel: ends every forward walk
 
-    // 4. mask rows
-    uint32_t* masks = reinterpret_cast<uint32_t*>(index + PredIndexLayout::kMasks);
-    const uint32_t total_words = (M + 1) * row_words;
-    for (uint32_t idx = tid; idx < total_words; idx += kBuildThreads) {
-        const uint32_t row = idx / row_words, c = idx - row * row_words;
-        const uint32_t start = row == 0 ? 0u : bp[row - 1];
-        uint32_t word = 0;
-#pragma unroll 4
-        for (uint32_t b = 0; b < 32; b++) {
-            const uint32_t k = c * 32 + b;  // K <= k < kMaxK: s_lo = 1 > s_hi = 0 -> never set
-            if (k < (uint32_t)kMaxK) word |= ((s_lo[k] <= start && start <= s_hi[k]) ? 1u : 0u) << b;
-        }
-        masks[idx] = word;
-    }
+    // 4. mask rows: filled by fill_masks_kernel (many CTAs) right after this kernel
 
     // 5. locator
     if (w <= kDirectMaxW) {
@@ -164,28 +144,65 @@ build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restr
     }
 }
 
-__global__ void __launch_bounds__(kBuildThreads, 1)
-counts_from_histogram_kernel(uint8_t* __restrict__ index, int K, unsigned long long* __restrict__ counts)
+// mask rows, one thread per 32-bit word: row i, word c, bit b  <-  lo_k <= start_i <= hi_k, k = 32c + b.
+// Reads the breakpoints back from the thresholds the build kernel wrote (bp = (thr + 1) >> (32 - w)).
+__global__ void __launch_bounds__(256)
+fill_masks_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, int K, int w,
+                  uint8_t* __restrict__ index)
 {
     const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(index + PredIndexLayout::kHeader);
     const uint32_t M = h->num_bp, row_words = h->row_words;
-    const uint32_t* masks = reinterpret_cast<const uint32_t*>(index + PredIndexLayout::kMasks);
-    unsigned long long* hist = reinterpret_cast<unsigned long long*>(index + PredIndexLayout::kHist);
-    for (uint32_t k = threadIdx.x; k < (uint32_t)K; k += kBuildThreads) {
-        unsigned long long c = 0;
-        for (uint32_t i = 0; i <= M; i++)
-            if ((masks[i * row_words + (k >> 5)] >> (k & 31)) & 1u) c += hist[i];
-        counts[k] += c;
+    const uint32_t* thr = reinterpret_cast<const uint32_t*>(index + PredIndexLayout::kThr);
+    uint32_t* masks = reinterpret_cast<uint32_t*>(index + PredIndexLayout::kMasks);
+    const uint32_t maxv = code_mask(w);
+    const uint32_t total_words = (M + 1) * row_words;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total_words; idx += gridDim.x * blockDim.x) {
+        const uint32_t row = idx / row_words, c = idx - row * row_words;
+        const uint32_t start = row == 0 ? 0u : ((thr[row - 1] + 1u) >> (32 - w));
+        uint32_t word = 0;
+        for (uint32_t b = 0; b < 32; b++) {
+            const uint32_t k = c * 32 + b;
+            if (k < (uint32_t)K) {
+                const uint32_t l = __ldg(lo + k);
+                uint32_t hh = __ldg(hi + k);
+                if (l <= hh && l <= maxv) {  // valid predicate (hi clamps to the domain)
+                    if (hh > maxv) hh = maxv;
+                    word |= ((l <= start && start <= hh) ? 1u : 0u) << b;
+                }
+            }
+        }
+        masks[idx] = word;
     }
+}
+
+// counts[k] += sum over intervals i of hist[i] * mask[i][k].  One CTA per 32 predicates; thread
+// (slice, p) sums the rows i = slice, slice + 32, ... for predicate p.  The histogram is cleared by
+// the next build_pred_index_kernel.
+__global__ void __launch_bounds__(1024)
+counts_from_histogram_kernel(const uint8_t* __restrict__ index, int K, unsigned long long* __restrict__ counts)
+{
+    __shared__ unsigned long long acc[32];
+    const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(index + PredIndexLayout::kHeader);
+    const uint32_t M = h->num_bp, row_words = h->row_words;
+    const uint32_t* masks = reinterpret_cast<const uint32_t*>(index + PredIndexLayout::kMasks);
+    const unsigned long long* hist = reinterpret_cast<const unsigned long long*>(index + PredIndexLayout::kHist);
+    const uint32_t p = threadIdx.x & 31, slice = threadIdx.x >> 5, c = blockIdx.x;
+    if (threadIdx.x < 32) acc[threadIdx.x] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i <= M; i += kBuildThreads) hist[i] = 0;
+    unsigned long long sum = 0;
+    for (uint32_t i = slice; i <= M; i += 32)
+        if ((masks[i * row_words + c] >> p) & 1u) sum += hist[i];
+    if (sum) atomicAdd(&acc[p], sum);
+    __syncthreads();
+    const uint32_t k = c * 32 + threadIdx.x;
+    if (threadIdx.x < 32 && k < (uint32_t)K) counts[k] += acc[threadIdx.x];
 }
 
 size_t pred_index_bytes() { return PredIndexLayout::kTotal; }
 
 cudaError_t launch_counts_from_histogram(void* d_index, int K, unsigned long long* d_counts, cudaStream_t stream)
 {
-    counts_from_histogram_kernel<<<1, kBuildThreads, 0, stream>>>(static_cast<uint8_t*>(d_index), K, d_counts);
+    counts_from_histogram_kernel<<<(K + 31) / 32, 1024, 0, stream>>>(static_cast<const uint8_t*>(d_index), K, d_counts);
     return cudaGetLastError();
 }
 
@@ -193,6 +210,8 @@ cudaError_t launch_build_pred_index(const uint32_t* d_lo, const uint32_t* d_hi, 
                                     cudaStream_t stream)
 {
     build_pred_index_kernel<<<1, kBuildThreads, 0, stream>>>(d_lo, d_hi, K, w, static_cast<uint8_t*>(d_index));
+    const unsigned words = (unsigned)((2 * K + 1) * pred_row_stride_words(K));
+    fill_masks_kernel<<<(words + 255) / 256, 256, 0, stream>>>(d_lo, d_hi, K, w, static_cast<uint8_t*>(d_index));
     return cudaGetLastError();
 }
 

@@ -260,4 +260,26 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32])
     for (int k = 0; k < 32; k += 2) exchange_bits<1>(a[k], a[k + 1]);
 }
 
+// ---- up to 8 predicates: 32 x 8 transpose --------------------------------------------------------
+// in : m[j] bits 0..7 = the predicates on code j.   out: r[k] bit j = predicate k on code j.
+// Four codes are packed per word so that byte b of word q is code 8b + q; the three bit stages then
+// leave predicate k's 32 results in word k already in code order -- 72 ops instead of 256.
+__device__ __forceinline__ void transpose32x8(const uint32_t (&m)[32], uint32_t (&r)[8])
+{
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const uint32_t lo = __byte_perm(m[q], m[q + 8], 0x0040);        // m[q].b0, m[q+8].b0
+        const uint32_t hi = __byte_perm(m[q + 16], m[q + 24], 0x0040);  // m[q+16].b0, m[q+24].b0
+        r[q] = __byte_perm(lo, hi, 0x5410);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) exchange_bits<4>(r[k], r[k + 4]);
+#pragma unroll
+    for (int g = 0; g < 8; g += 4)
+#pragma unroll
+        for (int k = g; k < g + 2; k++) exchange_bits<2>(r[k], r[k + 2]);
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) exchange_bits<1>(r[k], r[k + 1]);
+}
+
 }  // namespace sss

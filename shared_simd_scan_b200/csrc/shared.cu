@@ -93,28 +93,41 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
                 }
             }
             uint32_t* p = bitvecs + gb;  // this block's word of predicate 0; += stride_words per predicate
-            for (int c = 0; c < cols; c++) {
-                uint32_t m[32];
+            if (K <= 8) {  // one byte of predicates per code: the cheap 32 x 8 transpose
+                uint32_t m[32], r[8];
 #pragma unroll
-                for (int j = 0; j < 32; j++) m[j] = mask_word<kSmem>(ix, id[j], c);
-                transpose32(m);  // m[k'] bit j = predicate 32c+k' on code j
-                if (last) {
-                    const uint32_t keep = (1u << tail_bits) - 1u;
+                for (int j = 0; j < 32; j++) m[j] = mask_word<kSmem>(ix, id[j], 0);
+                transpose32x8(m, r);
+                const uint32_t keep = last ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
 #pragma unroll
-                    for (int k = 0; k < 32; k++) m[k] &= keep;
+                for (int k = 0; k < 8; k++) {
+                    if (k < K) st_stream_u32(p, r[k] & keep);
+                    p += stride_words;
                 }
-                const int kk = K - 32 * c;  // predicates in this column
-                if (kk >= 32) {
+            } else {
+                for (int c = 0; c < cols; c++) {
+                    uint32_t m[32];
 #pragma unroll
-                    for (int k = 0; k < 32; k++) {
-                        st_stream_u32(p, m[k]);
-                        p += stride_words;
+                    for (int j = 0; j < 32; j++) m[j] = mask_word<kSmem>(ix, id[j], c);
+                    transpose32(m);  // m[k'] bit j = predicate 32c+k' on code j
+                    if (last) {
+                        const uint32_t keep = (1u << tail_bits) - 1u;
+#pragma unroll
+                        for (int k = 0; k < 32; k++) m[k] &= keep;
                     }
-                } else {
+                    const int kk = K - 32 * c;  // predicates in this column
+                    if (kk >= 32) {
 #pragma unroll
-                    for (int k = 0; k < 32; k++) {
-                        if (k < kk) st_stream_u32(p, m[k]);
-                        p += stride_words;
+                        for (int k = 0; k < 32; k++) {
+                            st_stream_u32(p, m[k]);
+                            p += stride_words;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 32; k++) {
+                            if (k < kk) st_stream_u32(p, m[k]);
+                            p += stride_words;
+                        }
                     }
                 }
             }
