@@ -364,7 +364,7 @@ def extras(args, api, columns, n, peak):
         b.synchronize()
         return a.elapsed_time(b) / reps
 
-    out = {"shared": [], "unpack": []}
+    out = {"shared": [], "unpack": [], "pack": []}
     g = torch.Generator().manual_seed(42)
     for kind, w, K, logn in (("shared", 17, 8, 30), ("shared", 17, 64, 30), ("shared", 23, 64, 30),
                              ("linear", 9, 64, 30), ("linear", 9, 1024, 27)):
@@ -387,6 +387,16 @@ def extras(args, api, columns, n, peak):
         del buf
     n2 = 1 << min(28, args.logn)
     dec = torch.empty(n2, dtype=torch.int32, device="cuda")
+    # the compressor: int32 codes -> packed stream, 4 + w/8 bytes per code
+    for w in (1, 9, 17, 32):
+        api.decompress(columns[w], n2, w, out=dec)
+        repacked = torch.empty(api.packed_bytes(n2, w), dtype=torch.uint8, device="cuda")
+        ms = timed(lambda: api.compress(dec, w, out=repacked), reps=3, warm=2)
+        assert torch.equal(repacked[: n2 * w // 8], columns[w][: n2 * w // 8]), "pack(unpack(x)) != x"
+        b = n2 * (4 + w / 8)
+        out["pack"].append({"w": w, "n": n2, "ms": round(ms, 4), "gcodes_per_s": round(n2 / ms / 1e6, 1),
+                            "gb_per_s": round(b / ms / 1e6, 1), "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4)})
+        del repacked
     for w in WIDTHS:
         ms = timed(lambda: api.decompress(columns[w], n2, w, out=dec), reps=3, warm=2)
         b = n2 * (w / 8 + 4)

@@ -309,3 +309,60 @@ def test_many_predicates(sss, w, K):
     bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi)
     assert (host(bv)[:, :nb] == exp).all()
     assert (host(cnt).astype(np.uint64) == ecnt).all()
+
+
+@pytest.mark.parametrize("w,K", [(17, 64), (9, 64), (23, 8)])
+def test_shared_scan_full_size_properties(sss, w, K):
+    """2^28 codes: every shared-scan bitvector equals the single scan of its predicate (itself
+    oracle-checked above), counts equal, and the linear layout holds the same bits."""
+    n = 1 << 28
+    m = (1 << w) - 1
+    d_packed = sss.generate_packed(n, w, seed=42 + w)
+    g = torch.Generator().manual_seed(w * 131 + K)
+    lo = torch.randint(0, m + 1, (K,), generator=g)
+    hi = torch.clamp(lo + torch.randint(0, max(2, 2 * (m + 1) // K), (K,), generator=g), max=m)
+    hi[1] = lo[1]                      # an equality predicate
+    lo_l, hi_l = lo.tolist(), hi.tolist()
+    bvs, counts = sss.shared_scan(d_packed, n, w, lo_l, hi_l)
+    nb = n // 8
+    for k in sorted({0, 1, K // 2, K - 1}):
+        bv, c = sss.scan(d_packed, n, w, lo_l[k], hi_l[k])
+        assert torch.equal(bvs[k, :nb], bv[:nb]), (w, K, k)
+        assert int(counts[k].item()) == int(c.item())
+    if K * (n // 8) <= (1 << 31):
+        lin, lcounts = sss.shared_scan_linear(d_packed, n, w, lo_l, hi_l)
+        assert torch.equal(lcounts, counts)
+        for k in (1, K - 1):
+            assert torch.equal(lin[:nb, k].contiguous(), bvs[k, :nb])
+
+
+def test_c_abi_argument_errors(sss):
+    """The boundary reports bad arguments with status codes instead of faulting."""
+    import ctypes as C
+    from shared_simd_scan_b200 import _lib
+    L = _lib.lib()
+    ctx = sss.Context.current().handle
+    buf = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    st = L.sss_scan_range(ctx, buf.data_ptr(), 100, 0, 1, 2, out.data_ptr(), None, None)
+    assert st == -1                                      # w = 0
+    st = L.sss_scan_range(ctx, buf.data_ptr(), 100, 33, 1, 2, out.data_ptr(), None, None)
+    assert st == -1                                      # w = 33
+    st = L.sss_scan_range(ctx, buf.data_ptr() + 4, 100, 9, 1, 2, out.data_ptr(), None, None)
+    assert st == -1                                      # packed not 16-byte aligned
+    st = L.sss_scan_range(ctx, None, 100, 9, 1, 2, out.data_ptr(), None, None)
+    assert st == -1
+    lo = torch.zeros(2048, dtype=torch.int32, device="cuda")
+    st = L.sss_shared_scan(ctx, buf.data_ptr(), 100, 9, lo.data_ptr(), lo.data_ptr(), 1025, out.data_ptr(), 64, None, None)
+    assert st == -1                                      # K > SSS_MAX_PREDICATES
+    st = L.sss_shared_scan(ctx, buf.data_ptr(), 100, 9, lo.data_ptr(), lo.data_ptr(), 4, out.data_ptr(), 6, None, None)
+    assert st == -1                                      # stride not a multiple of 4 / too small
+    h = C.c_uint64(0)
+    st = L.sss_host_scan_range(ctx, buf.cpu().numpy().ctypes.data, 100, 9, 1, 2, 5, out.cpu().numpy().ctypes.data, C.byref(h))
+    assert st == -1                                      # unknown tail mode
+    assert b"invalid" in L.sss_error_string(-1)
+    # n == 0 is legal and touches nothing
+    cnt = torch.full((1,), 7, dtype=torch.int64, device="cuda")
+    assert L.sss_scan_range(ctx, buf.data_ptr(), 0, 9, 1, 2, out.data_ptr(), cnt.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == 0 and not out.any()
