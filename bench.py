@@ -364,7 +364,7 @@ def extras(args, api, columns, n, peak):
         b.synchronize()
         return a.elapsed_time(b) / reps
 
-    out = {"shared": [], "unpack": [], "pack": []}
+    out = {"shared": [], "unpack": [], "pack": [], "positions": []}
     g = torch.Generator().manual_seed(42)
     for kind, w, K, logn in (("shared", 17, 8, 30), ("shared", 17, 64, 30), ("shared", 23, 64, 30),
                              ("linear", 9, 64, 30), ("linear", 9, 1024, 27)):
@@ -385,6 +385,22 @@ def extras(args, api, columns, n, peak):
                               "gcodes_per_s": round(nn / ms / 1e6, 2), "gb_per_s": round(b / ms / 1e6, 1),
                               "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4)})
         del buf
+    # ascending position list from the scan's bitvector, at three selectivities (w = 17)
+    w = 17
+    m = (1 << w) - 1
+    bv = torch.empty(api.bitvec_bytes(n), dtype=torch.uint8, device="cuda")
+    cnt1 = torch.empty(1, dtype=torch.int64, device="cuda")
+    for sel in (0.001, 0.01, 0.25):
+        hi_v = max(0, int(sel * (m + 1)) - 1)
+        api.scan(columns[w], n, w, 0, hi_v, out=bv, count=cnt1)
+        hits = int(cnt1.item())
+        api.positions(bv, n, capacity=hits)  # sizes the context workspace outside the timed region
+        ms = timed(lambda: api.positions(bv, n, capacity=hits), reps=3, warm=1)
+        b = 2 * n / 8 + 8.0 * hits
+        out["positions"].append({"w": w, "n": n, "selectivity": sel, "hits": hits, "ms": round(ms, 4),
+                                 "gcodes_per_s": round(n / ms / 1e6, 1), "gb_per_s": round(b / ms / 1e6, 1),
+                                 "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4)})
+    del bv
     n2 = 1 << min(28, args.logn)
     dec = torch.empty(n2, dtype=torch.int32, device="cuda")
     # the compressor: int32 codes -> packed stream, 4 + w/8 bytes per code

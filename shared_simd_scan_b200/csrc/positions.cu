@@ -101,6 +101,11 @@ pos_scan_kernel(const uint32_t* __restrict__ tile_counts, uint64_t tiles, unsign
     if (threadIdx.x == 0 && num != nullptr) *num = carry_s;
 }
 
+// Ordered expansion.  A tile is 1024 bitvector words; warp w owns words [128w, 128w+128) in four
+// rounds of 32 (lane l loads word l of the round, coalesced).  Within a round the words are walked
+// one at a time by the whole warp: lane l owns bit l, its rank among the set bits below it is a
+// popcount, so the set bits of a word are written by one store instruction to consecutive slots --
+// ascending order and coalesced stores at any selectivity.  All-zero words are skipped via a ballot.
 __global__ void __launch_bounds__(kThreads)
 pos_expand_kernel(const uint32_t* __restrict__ bitvec, uint64_t n, uint64_t tiles,
                   const unsigned long long* __restrict__ tile_offsets, uint64_t base,
@@ -110,37 +115,61 @@ pos_expand_kernel(const uint32_t* __restrict__ bitvec, uint64_t n, uint64_t tile
     const uint64_t n_words = (n + 31) >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t below = (1u << lane) - 1u;
     for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const uint64_t w0 = tile * kPosTileWords + threadIdx.x * kPosWordsPerThread;
-        uint32_t v[kPosWordsPerThread];
+        const uint64_t w0 = tile * kPosTileWords + warp * 128;
+        uint32_t v[4];
         uint32_t c = 0;
 #pragma unroll
-        for (int i = 0; i < kPosWordsPerThread; i++) {
-            v[i] = load_word(bitvec, w0 + i, n_words, tail_bits);
-            c += __popc(v[i]);
+        for (int r = 0; r < 4; r++) {
+            v[r] = load_word(bitvec, w0 + r * 32 + lane, n_words, tail_bits);
+            c += __popc(v[r]);
         }
-        uint32_t incl = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        if (lane == 0) warp_tot[warp] = c;
         __syncthreads();
         uint32_t before = 0;
 #pragma unroll
         for (int i = 0; i < kWarps; i++) before += (i < (int)warp) ? warp_tot[i] : 0u;
-        uint64_t o = tile_offsets[tile] + before + (incl - c);
+        uint64_t o = tile_offsets[tile] + before;  // first output slot of this warp's words
 #pragma unroll
-        for (int i = 0; i < kPosWordsPerThread; i++) {
-            uint32_t bits = v[i];
-            const uint64_t code0 = base + (w0 + i) * 32;
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (o < capacity) positions[o] = code0 + b;
-                o++;
+        for (int r = 0; r < 4; r++) {
+            // exclusive prefix of the words' popcounts across the lanes of this round
+            const uint32_t pc = __popc(v[r]);
+            uint32_t incl = pc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (uint32_t)d) incl += t;
             }
+            const uint32_t excl = incl - pc;
+            const uint32_t round_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (round_total > 96) {
+                // dense round: walk the words, one coalesced store per non-empty word
+                uint32_t nonzero = __ballot_sync(0xFFFFFFFFu, v[r] != 0);
+                while (nonzero) {
+                    const int i = __ffs(nonzero) - 1;
+                    nonzero &= nonzero - 1;
+                    const uint32_t word = __shfl_sync(0xFFFFFFFFu, v[r], i);
+                    const uint32_t start = __shfl_sync(0xFFFFFFFFu, excl, i);
+                    if ((word >> lane) & 1u) {
+                        const uint64_t slot = o + start + __popc(word & below);
+                        if (slot < capacity) positions[slot] = base + (w0 + (uint64_t)r * 32 + i) * 32 + lane;
+                    }
+                }
+            } else {
+                // sparse round (<= 3 set bits per word on average): every lane expands its own word
+                uint32_t bits = v[r];
+                uint64_t slot = o + excl;
+                const uint64_t code0 = base + (w0 + (uint64_t)r * 32 + lane) * 32;
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (slot < capacity) positions[slot] = code0 + b;
+                    slot++;
+                }
+            }
+            o += round_total;
         }
         __syncthreads();
     }
