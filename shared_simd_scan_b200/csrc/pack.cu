@@ -2,13 +2,24 @@
 //
 // sss_pack replaces compress_9bit_input (reference src/simd_scan_compression.cpp:53-104) for any
 // width 1..32 and uint32 codes: code i occupies stream bits [i*w, (i+1)*w), little-endian.  The
-// reference scatters each code into one or two uint64 words with a serial cursor; here every thread
-// owns one 32-bit OUTPUT word and gathers the (at most 32/w + 2) codes that overlap it, so there
-// are no write conflicts and stores are fully coalesced.
+// reference scatters each code into one or two uint64 words with a serial cursor.
 //
-// sss_generate_packed produces the benchmark column (uniform codes from a counter-based
-// SplitMix64) directly in packed form, with no unpacked copy in HBM -- the 2^30..2^34-code columns
-// of BASELINE.json never exist unpacked.
+// pack_block_kernel<W> (full 32-code blocks): a thread packs one block = 32 codes -> W words with
+// compile-time shifts.  Both sides of that are strided per thread (128 bytes in, 4W bytes out), so
+// both go through a per-warp shared-memory transposition: the warp loads its 1024 codes with
+// coalesced 16-byte loads, parks them in a [32 blocks][8+1 chunks] padded array (conflict-free both
+// ways), each thread reads back its own block, packs, parks its W words at an odd word pitch, and the
+// warp streams the 32*W words out as whole 128-byte lines.
+//
+// pack_kernel<Source> (generic, runtime w): one thread per OUTPUT word gathering the codes that
+// overlap it.  Used for the ragged tail of sss_pack and for sss_generate_packed, which produces the
+// benchmark column (uniform codes from a counter-based SplitMix64) directly in packed form -- the
+// 2^30..2^34-code columns of BASELINE.json never exist unpacked.
+//
+// Roofline: HBM.  Algorithmic bytes per code = 4 + W/8.
+#include <array>
+#include <utility>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -36,13 +47,15 @@ struct FromGenerator {
     }
 };
 
+// ---- generic: one thread per output word ---------------------------------------------------------
+
 template <class Source>
 __global__ void __launch_bounds__(kThreads)
-pack_kernel(Source src, uint64_t n, int w, uint32_t* __restrict__ packed, uint64_t packed_words)
+pack_kernel(Source src, uint64_t n, int w, uint32_t* __restrict__ packed, uint64_t first_word, uint64_t end_word)
 {
     const uint32_t mask = code_mask(w);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t word = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; word < packed_words; word += stride) {
+    for (uint64_t word = first_word + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; word < end_word; word += stride) {
         const uint64_t bit0 = word * 32;
         uint64_t c = bit0 / (uint64_t)w;  // first code overlapping this word
         uint32_t acc = 0;
@@ -56,6 +69,98 @@ pack_kernel(Source src, uint64_t n, int w, uint32_t* __restrict__ packed, uint64
     }
 }
 
+// ---- full blocks: one thread per 32-code block, warp-level transposition through shared memory ----
+
+template <int W, int J>
+struct PackBlock {
+    static __device__ __forceinline__ void run(const uint32_t (&c)[32], uint32_t (&out)[W])
+    {
+        constexpr CodeSlot s = code_slot(W, J);
+        const uint32_t v = c[J] & code_mask(W);
+        if constexpr (s.shift == 0) {
+            out[s.first_word] = v;  // the first code to touch this word
+        } else {
+            out[s.first_word] |= v << s.shift;
+        }
+        if constexpr (s.straddles) out[s.last_word] = v >> (32 - s.shift);
+        PackBlock<W, J + 1>::run(c, out);
+    }
+};
+template <int W>
+struct PackBlock<W, 32> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[W]) {}
+};
+
+constexpr int kPackWarps = 4;  // 128-thread CTAs: 4 warps x (codes 4608 B + words <= 4224 B) of shared memory
+
+template <int W>
+__global__ void __launch_bounds__(kPackWarps * 32)
+pack_block_kernel(const uint32_t* __restrict__ codes, uint64_t n_full_blocks, uint32_t* __restrict__ packed)
+{
+    constexpr int WP = W | 1;                                   // odd word pitch: conflict-free block rows
+    __shared__ __align__(16) uint4 s_codes[kPackWarps][32 * 9];  // [block][8 chunks + 1 pad]
+    __shared__ uint32_t s_words[kPackWarps][32 * WP];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t warps_total = (uint64_t)gridDim.x * kPackWarps;
+    const uint64_t groups = (n_full_blocks + 31) / 32;  // a warp packs 32 blocks = 1024 codes per round
+    for (uint64_t g = (uint64_t)blockIdx.x * kPackWarps + warp; g < groups; g += warps_total) {
+        const uint64_t block0 = g * 32;
+        const uint32_t nb = (uint32_t)((n_full_blocks - block0) < 32 ? (n_full_blocks - block0) : 32);  // blocks here
+        const uint4* src = reinterpret_cast<const uint4*>(codes + block0 * 32);
+        // coalesced load of nb*8 chunks; chunk c -> block c/8, slot c%8
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t c = i * 32 + lane;
+            if (c < nb * 8) s_codes[warp][(c >> 3) * 9 + (c & 7)] = __ldcs(src + c);
+        }
+        __syncwarp();
+        uint32_t out[W];
+        if (lane < nb) {
+            uint32_t cds[32];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint4 v = s_codes[warp][lane * 9 + q];
+                cds[4 * q + 0] = v.x;
+                cds[4 * q + 1] = v.y;
+                cds[4 * q + 2] = v.z;
+                cds[4 * q + 3] = v.w;
+            }
+            PackBlock<W, 0>::run(cds, out);
+#pragma unroll
+            for (int k = 0; k < W; k++) s_words[warp][lane * WP + k] = out[k];
+        }
+        __syncwarp();
+        // stream the nb*W words out, 128 bytes per warp store
+        uint32_t* dst = packed + block0 * W;
+        const uint32_t total = nb * W;
+        for (uint32_t idx = lane; idx < total; idx += 32) {
+            const uint32_t b = idx / W, k = idx - b * W;
+            __stcs(dst + idx, s_words[warp][b * WP + k]);
+        }
+        __syncwarp();
+    }
+}
+
+template <int W>
+static cudaError_t launch_block_w(const Device& dev, const uint32_t* codes, uint64_t n_full_blocks, uint32_t* packed,
+                                  cudaStream_t stream)
+{
+    const uint64_t groups = (n_full_blocks + 31) / 32;
+    const uint64_t want = (groups + kPackWarps - 1) / kPackWarps;
+    const uint64_t cap = (uint64_t)dev.sm_count * 12;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    pack_block_kernel<W><<<grid, kPackWarps * 32, 0, stream>>>(codes, n_full_blocks, packed);
+    return cudaGetLastError();
+}
+
+using PackLauncher = cudaError_t (*)(const Device&, const uint32_t*, uint64_t, uint32_t*, cudaStream_t);
+
+template <int... Ws>
+static constexpr auto make_table(std::integer_sequence<int, Ws...>)
+{
+    return std::array<PackLauncher, sizeof...(Ws)>{&launch_block_w<Ws + 1>...};
+}
+
 static unsigned grid_for(const Device& dev, uint64_t items)
 {
     const uint64_t want = (items + kThreads - 1) / kThreads;
@@ -66,7 +171,18 @@ static unsigned grid_for(const Device& dev, uint64_t items)
 cudaError_t launch_pack(const Device& dev, const uint32_t* codes, uint64_t n, int w, uint32_t* packed,
                         uint64_t packed_words, cudaStream_t stream)
 {
-    pack_kernel<<<grid_for(dev, packed_words), kThreads, 0, stream>>>(FromArray{codes}, n, w, packed, packed_words);
+    static constexpr auto table = make_table(std::make_integer_sequence<int, 32>{});
+    // full 32-code blocks through the block kernel (needs 16-byte aligned codes), the ragged tail
+    // and the zero padding through the generic one
+    uint64_t full_blocks = (reinterpret_cast<uintptr_t>(codes) & 15) == 0 ? n / 32 : 0;
+    if (full_blocks) {
+        cudaError_t e = table[w - 1](dev, codes, full_blocks, packed, stream);
+        if (e != cudaSuccess) return e;
+    }
+    const uint64_t first_word = full_blocks * (uint64_t)w;
+    if (first_word < packed_words)
+        pack_kernel<<<grid_for(dev, packed_words - first_word), kThreads, 0, stream>>>(FromArray{codes}, n, w, packed,
+                                                                                      first_word, packed_words);
     return cudaGetLastError();
 }
 
@@ -74,7 +190,7 @@ cudaError_t launch_generate_packed(const Device& dev, uint32_t* packed, uint64_t
                                    uint64_t seed, uint64_t first_index, cudaStream_t stream)
 {
     pack_kernel<<<grid_for(dev, packed_words), kThreads, 0, stream>>>(FromGenerator{seed, first_index}, n, w, packed,
-                                                                     packed_words);
+                                                                     0, packed_words);
     return cudaGetLastError();
 }
 
