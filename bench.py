@@ -148,6 +148,59 @@ def cpu_reference_sweep(logn, reps, threads):
     return len(WIDTHS) * n / total, per_w, kind
 
 
+def cpu_reference_detail(threads):
+    """The other BASELINE.json configs on the host cores, scaled: codes/s is
+    size-independent beyond cache.  Unmodified reference via oracle/_ref; [] when it is not built."""
+    import ctypes as C
+
+    import numpy as np
+    from oracle import binding as B
+    if not all(B.ref_available(w) for w in (9, 11, 17)):
+        return []
+    rng = np.random.default_rng(7)
+    rows = []
+
+    def column(w, n):
+        packed = np.zeros(B.compressed_buffer_size(w, n), dtype=np.uint8)
+        packed[: n * w // 8] = np.frombuffer(rng.bytes(n * w // 8), dtype=np.uint8)
+        return packed
+
+    # cfg 1: single predicate, 2^24 x 11 bit, the reference AVX2 scan, one thread and all threads
+    w, n = 11, 1 << 24
+    packed = column(w, n)
+    hits = C.c_longlong(0)
+    for t in (1, threads):
+        sec = B.ref(w).ref_time_scan(B.SCAN["256_unrolled"], 3, packed.ctypes.data, n, t, 5, C.byref(hits))
+        rows.append({"config": "cfg1 scan 2^24 x 11 bit", "variant": "scan_256_unrolled", "threads": t,
+                     "gcodes_per_s": round(n / sec / 1e9, 2)})
+    # cfg 2 sample: decompression
+    for w, variant in ((9, "256_avx2"), (17, "128_unrolled")):
+        n = 1 << 25
+        packed = column(w, n)
+        sec = B.ref(w).ref_time_decompress(B.DECOMPRESS[variant], packed.ctypes.data, n, threads, 3)
+        rows.append({"config": f"cfg2 unpack 2^25 x {w} bit", "variant": "decompress_" + variant, "threads": threads,
+                     "gcodes_per_s": round(n / sec / 1e9, 2)})
+    # cfg 3 / 5 scaled: shared scan K = 64
+    w, n, K = 17, 1 << 22, 64
+    packed = column(w, n)
+    keys = np.ascontiguousarray(rng.integers(0, 1 << w, size=K), dtype=np.int32)
+    for name, fn in (("shared_scan_128_standard", lambda: B.ref(w).ref_time_shared_scan(
+            B.SHARED["128_standard"], keys.ctypes.data, K, packed.ctypes.data, n, threads, 2)),
+                     ("shared_scan_128_linear_standard", lambda: B.ref(w).ref_time_shared_scan_linear(
+                         B.LINEAR["linear_standard"], keys.ctypes.data, K, packed.ctypes.data, n, threads, 2))):
+        rows.append({"config": "cfg3 shared scan K=64, 2^22 x 17 bit", "variant": name, "threads": threads,
+                     "gcodes_per_s": round(n / fn() / 1e9, 3)})
+    # cfg 4 scaled: linear shared scan K = 1024, 9 bit
+    w, n, K = 9, 1 << 19, 1024
+    packed = column(w, n)
+    keys = np.ascontiguousarray(np.arange(K) % 512, dtype=np.int32)
+    sec = B.ref(w).ref_time_shared_scan_linear(B.LINEAR["linear_standard"], keys.ctypes.data, K, packed.ctypes.data, n,
+                                               threads, 2)
+    rows.append({"config": "cfg4 linear shared scan K=1024, 2^19 x 9 bit", "variant": "shared_scan_128_linear_standard",
+                 "threads": threads, "gcodes_per_s": round(n / sec / 1e9, 4)})
+    return rows
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -337,6 +390,7 @@ def run_ours(args):
             "sample": f"same sweep on 2^{args.cpu_logn} uniform codes per width (best of 2), equality key 3; "
                       "scan_256_unrolled (w<=16) / scan_128_unrolled (w>16) of the unmodified reference, column "
                       f"range-partitioned over {threads} host threads; {time.perf_counter() - t0:.1f} s of wall time"}
+        line["cpu_reference_detail"] = cpu_reference_detail(threads)
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
