@@ -163,11 +163,14 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
             dep |= id;
             if (count_matches && lane < valid) atomicAdd(&s_hist[id], 1u);
             uint32_t m[32];
+            const uint32_t row_off = id * ix.row_words * 4;  // my code's mask row, in bytes
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const uint32_t idj = __shfl_sync(0xFFFFFFFFu, id, j);
-                m[j] = mask_word<kSmem>(ix, idj, my_col);
-                if ((uint32_t)j >= valid) m[j] = 0;  // codes past n contribute zero bits
+            for (int j = 0; j < 32; j++)
+                m[j] = mask_word_at<kSmem>(ix, __shfl_sync(0xFFFFFFFFu, row_off, j), 4 * my_col);
+            if (valid != 32) {  // only the column's last block: codes past n contribute zero bits
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if ((uint32_t)j >= valid) m[j] = 0;
             }
             exchange_linear(m);
             if (kk > 0) {

@@ -209,6 +209,21 @@ __device__ __forceinline__ uint32_t mask_word(const PredIndexView& ix, uint32_t 
     }
 }
 
+// Same with the row already resolved to a byte offset (id * row_words * 4) and the column to bytes:
+// lets a caller hoist the multiply out of its inner loop.
+template <bool kSmem>
+__device__ __forceinline__ uint32_t mask_word_at(const PredIndexView& ix, uint32_t row_byte_offset, uint32_t col_bytes)
+{
+    if constexpr (kSmem) {
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ix.masks_saddr + row_byte_offset + col_bytes));
+        return v;
+    } else {
+        return __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(ix.masks) + row_byte_offset +
+                                                       col_bytes));
+    }
+}
+
 // ---- 32 x 32 bit-matrix transpose in registers ------------------------------------------------------
 
 // (a & m) | (b & ~m) in ONE LOP3 (ptxas does not fuse the two-immediate form on its own)
