@@ -23,6 +23,8 @@
  *  - Counts and positions are 64-bit (the reference's `int hits` overflows past 2^31 codes).
  *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device entry points
  *    only enqueue work; host entry points (sss_host_*) are synchronous.
+ *  - A context is not thread-safe: use it from one host thread at a time (one context per thread
+ *    is fine), and it serves one shared scan at a time (its predicate index lives in the context).
  *  - Return value: SSS_OK, a negative SSS_ERR_* argument error, or 1000 + cudaError_t.
  *    There is no CPU fallback: without a CUDA device every compute entry point fails.
  */
