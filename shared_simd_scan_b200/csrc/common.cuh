@@ -89,6 +89,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
+// 256-bit store (sm_100: STG.E.256): one full 32-byte sector per lane.  p must be 32-byte aligned.
+__device__ __forceinline__ void st_v8_u32(void* p, const uint32_t (&w)[8])
+{
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                 "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+
 // streaming stores: results are written once and never re-read by these kernels
 __device__ __forceinline__ void st_stream_u32(uint32_t* p, uint32_t v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream_v4(int4* p, int4 v) { __stcs(p, v); }

@@ -78,9 +78,12 @@ __device__ __forceinline__ void exchange_linear(uint32_t (&a)[32])
 
 // 32 consecutive predicate bytes of one output row (8 words, already in row order); kk = predicates
 // that exist in this column (>= 32: all)
-__device__ __forceinline__ void store_row_piece(uint8_t* dst, const uint32_t (&ws)[8], int kk, bool vec16, bool vec4)
+__device__ __forceinline__ void store_row_piece(uint8_t* dst, const uint32_t (&ws)[8], int kk, bool vec32, bool vec16,
+                                                bool vec4)
 {
-    if (vec16 && kk >= 32) {
+    if (vec32 && kk >= 32) {
+        st_v8_u32(dst, ws);
+    } else if (vec16 && kk >= 32) {
         __stcs(reinterpret_cast<uint4*>(dst), make_uint4(ws[0], ws[1], ws[2], ws[3]));
         __stcs(reinterpret_cast<uint4*>(dst) + 1, make_uint4(ws[4], ws[5], ws[6], ws[7]));
     } else {
@@ -144,6 +147,7 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const int cols = (K + 31) >> 5;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool vec32 = (K & 31) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0;
     const bool vec16 = (K & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const bool vec4 = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
     const int my_col = (int)lane < cols ? (int)lane : 0;   // lanes past the last column idle along
@@ -179,7 +183,7 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
                 for (int i = 0; i < 4; i++) {
                     const uint32_t ws[8] = {m[8 * i + 0], m[8 * i + 4], m[8 * i + 1], m[8 * i + 5],
                                             m[8 * i + 2], m[8 * i + 6], m[8 * i + 3], m[8 * i + 7]};
-                    store_row_piece(row0 + (uint64_t)i * K, ws, kk, vec16, vec4);
+                    store_row_piece(row0 + (uint64_t)i * K, ws, kk, vec32, vec16, vec4);
                 }
             }
         }
@@ -211,6 +215,7 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const int cols = (K + 31) >> 5;
     // widest store the row pitch K and the base alignment allow
+    const bool vec32 = (K & 31) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0;
     const bool vec16 = (K & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const bool vec4 = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
 
@@ -262,7 +267,7 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
                     // word q of the row = m[8i + 4*(q&1) + (q>>1)]
                     const uint32_t ws[8] = {m[8 * i + 0], m[8 * i + 4], m[8 * i + 1], m[8 * i + 5],
                                             m[8 * i + 2], m[8 * i + 6], m[8 * i + 3], m[8 * i + 7]};
-                    store_row_piece(dst, ws, kk, vec16, vec4);
+                    store_row_piece(dst, ws, kk, vec32, vec16, vec4);
                 }
             }
         }
