@@ -85,7 +85,8 @@ int sss_pack(sss_ctx* ctx, const uint32_t* d_codes, uint64_t n, int w, void* d_p
 int sss_generate_packed(sss_ctx* ctx, void* d_packed, uint64_t n, int w, uint64_t seed,
                         uint64_t first_index, void* stream);
 
-/* decompress_* (src/simd_scan_decompression.cpp:6-470): one zero-extended int32 per code. */
+/* decompress_* (src/simd_scan_decompression.cpp:6-470): one zero-extended int32 per code.
+ * d_out must be 32-byte aligned (the kernel writes 256-bit vectors). */
 int sss_unpack(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, int32_t* d_out, void* stream);
 
 /* scan_* (src/simd_scan.cpp:20-306) generalised to a range.  *d_count is overwritten with the

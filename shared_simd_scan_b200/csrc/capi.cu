@@ -247,7 +247,7 @@ int sss_generate_packed(sss_ctx* ctx, void* d_packed, uint64_t n, int w, uint64_
 int sss_unpack(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, int32_t* d_out, void* stream)
 {
     SSS_TRY(check_common(ctx, d_packed, w));
-    if (d_out == nullptr || (reinterpret_cast<uintptr_t>(d_out) & 15)) return SSS_ERR_INVALID_ARG;
+    if (d_out == nullptr || (reinterpret_cast<uintptr_t>(d_out) & 31)) return SSS_ERR_INVALID_ARG;  // 256-bit stores
     if (n == 0) return SSS_OK;
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return cuda_status(launch_unpack(ctx->dev, d_packed, n, w, d_out, static_cast<cudaStream_t>(stream)));

@@ -2,9 +2,9 @@
 //
 // Replaces the nine decompress_* variants (reference src/simd_scan_decompression.cpp:6-470:
 // movdqu + pshufb + pmulld/psrld or vpsrlvd + store).  The kernel is write-dominated (4 bytes out
-// per W/8 bytes in), so the thread mapping is chosen for the stores: each lane owns 4 consecutive
-// codes and writes them with one 16-byte streaming store, a warp therefore writes 512 contiguous
-// bytes per instruction.  Codes are pulled out of the shared-memory tile with a word pair + funnel
+// per W/8 bytes in), so the thread mapping is chosen for the stores: each lane owns 8 consecutive
+// codes and writes them with one 256-bit store (sm_100 STG.E.256: a full 32-byte sector per lane), a
+// warp therefore writes 1 KB of contiguous output per instruction.  Codes are pulled out of the shared-memory tile with a word pair + funnel
 // shift (SHF.R.W), which is exact for every width 1..32 (the reference's 4-byte gather is not,
 // SURVEY.md Appendix B).
 //
@@ -19,8 +19,8 @@ namespace sss {
 
 template <int W>
 struct UnpackCfg {
-    static constexpr int kCodesPerThread = 4;
-    static constexpr int kR = 8;                                             // 4-code groups per thread per tile
+    static constexpr int kCodesPerThread = 8;                                // one 32-byte (256-bit) store per lane
+    static constexpr int kR = 4;                                             // 8-code groups per thread per tile
     static constexpr int kCodesPerTile = kThreads * kCodesPerThread * kR;    // 8192
     static constexpr int kTileBytes = kCodesPerTile / 32 * W * 4;            // 1 KB * W
     static constexpr int kStages = ring_stages(kTileBytes);
@@ -47,19 +47,19 @@ unpack_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64
             const uint32_t c0 = (r * kThreads + threadIdx.x) * Cfg::kCodesPerThread;  // code index in tile
             const uint64_t g0 = tile_code0 + c0;
             if (g0 < n) {
-                uint32_t v[4];
+                uint32_t v[8];
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
+                for (int e = 0; e < 8; e++) {
                     const uint32_t bit = (c0 + e) * W;
                     const uint32_t wi = bit >> 5;
                     // buf[wi + 1] is only significant when the code straddles; the stage carries a
                     // 16-byte pad so the read is always inside shared memory
                     v[e] = __funnelshift_r(buf[wi], buf[wi + 1], bit & 31) & mask;
                 }
-                if (g0 + 4 <= n) {
-                    st_stream_v4(reinterpret_cast<int4*>(out + g0), make_int4(v[0], v[1], v[2], v[3]));
+                if (g0 + 8 <= n) {
+                    st_v8_u32(out + g0, v);
                 } else {
-                    for (int e = 0; e < 4 && g0 + e < n; e++) out[g0 + e] = (int32_t)v[e];
+                    for (int e = 0; e < 8 && g0 + e < n; e++) out[g0 + e] = (int32_t)v[e];
                 }
             }
         }
