@@ -245,6 +245,73 @@ def workload_config(args):
 # our arm
 # ---------------------------------------------------------------------------------------------
 
+def run_cfg5(args):
+    """Optional workload (not the contract line): BASELINE configs[4] -- shared scan, K = 64 range
+    predicates over 23-bit codes, the column range-sharded over the ranks (2^31 codes per GPU = 16 Gi
+    codes on 8 GPUs), per-query counts combined with one NCCL all-reduce.  `--workload cfg5`."""
+    import torch
+    import torch.distributed as dist
+
+    from shared_simd_scan_b200 import api
+    from shared_simd_scan_b200 import dist as sdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w, K = 23, 64
+    n_per = 1 << args.cfg5_logn
+    shard = sdist.generate_shard(n_per * world, w, seed=42 + w)
+    m = (1 << w) - 1
+    g = torch.Generator().manual_seed(42)
+    lo = torch.randint(0, m + 1, (K,), generator=g)
+    hi = torch.clamp(lo + torch.randint(0, 2 * (m + 1) // K, (K,), generator=g), max=m)
+    lo_d, hi_d = lo.to(torch.int32).cuda(), hi.to(torch.int32).cuda()
+    out = torch.empty((K, (api.bitvec_bytes(shard.count) + 15) // 16 * 16), dtype=torch.uint8, device="cuda")
+    counts = torch.empty(K, dtype=torch.int64, device="cuda")
+
+    def step():
+        api.shared_scan(shard.packed, shard.count, w, lo_d, hi_d, out=out, counts=counts)
+        if world > 1:
+            dist.all_reduce(counts)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step()
+    b.record()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    peak, _ = measured_peak()
+    bytes_per_gpu = shard.count * (w / 8 + K / 8)
+    if rank == 0:
+        print(json.dumps({
+            "workload": f"cfg5: shared scan K=64 over {world} x 2^{args.cfg5_logn} 23-bit codes, range-sharded, "
+                        "NCCL all-reduce of the 64 counts", "n_gpus": world, "steps": args.steps, "ms_per_step": ms,
+            "value": world * shard.count / (ms * 1e-3), "unit": "codes/s", "scaling": "weak",
+            "per_gpu_gb_per_s": round(bytes_per_gpu / ms / 1e6, 1),
+            "per_gpu_frac_of_measured_peak": round(bytes_per_gpu / ms / 1e6 / peak, 4),
+            "global_count_of_query_0": int(counts[0].item())}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -485,11 +552,16 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-logn", type=int, default=27, help="cpu_baseline sample: log2 codes per width")
     ap.add_argument("--ref-logn", type=int, default=26, help="--impl reference sample: log2 codes per width per step")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "cfg5"],
+                    help="sweep = the contract line; cfg5 = optional sharded shared scan (K=64, 23 bit)")
+    ap.add_argument("--cfg5-logn", type=int, default=31, help="cfg5: log2 codes per GPU")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "cfg5":
+        return run_cfg5(args)
     return run_ours(args)
 
 
