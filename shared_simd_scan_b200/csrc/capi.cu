@@ -16,6 +16,7 @@ using namespace sss;
 namespace {
 
 constexpr int kSlots = 3;                       // host<->device staging ring depth
+constexpr uint32_t kCountSlots = 1024;          // scans in flight that may count concurrently
 constexpr uint64_t kChunkBytes = 64ull << 20;   // target bytes per staged chunk (larger of in/out)
 
 struct Slot {
@@ -51,6 +52,8 @@ struct sss_ctx {
     void* d_ws = nullptr;                    // positions workspace
     size_t ws_cap = 0;
     void* d_index = nullptr;                 // predicate index of the shared scan in flight (predindex.cuh)
+    unsigned long long* d_count_slots = nullptr;  // kCountSlots x {accumulator, ticket}, zero between launches
+    uint32_t next_count_slot = 0;
 };
 
 namespace {
@@ -175,6 +178,8 @@ int sss_ctx_create(int device, sss_ctx** out)
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_hi, SSS_MAX_PREDICATES * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counts, (SSS_MAX_PREDICATES + 1) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_index, pred_index_bytes());
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_count_slots, kCountSlots * 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_count_slots, 0, kCountSlots * 2 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         sss_ctx_destroy(ctx);
         return cuda_status(e);
@@ -197,6 +202,7 @@ int sss_ctx_destroy(sss_ctx* ctx)
     if (ctx->d_counts) cudaFree(ctx->d_counts);
     if (ctx->d_ws) cudaFree(ctx->d_ws);
     if (ctx->d_index) cudaFree(ctx->d_index);
+    if (ctx->d_count_slots) cudaFree(ctx->d_count_slots);
     delete ctx;
     return SSS_OK;
 }
@@ -254,13 +260,16 @@ int sss_unpack(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, int32_t* d
 }
 
 static int scan_range_impl(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32_t lo, uint32_t hi,
-                           void* d_bitvec, unsigned long long* d_count, bool zero_count, cudaStream_t st)
+                           void* d_bitvec, unsigned long long* d_count, bool accumulate, cudaStream_t st)
 {
-    if (d_count && zero_count) SSS_CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
-    if (n == 0) return SSS_OK;
     const AlignedRange r = aligned_range(w, lo, hi);
-    if (r.empty) return cuda_status(cudaMemsetAsync(d_bitvec, 0, 4 * ((n + 31) / 32), st));
-    return cuda_status(launch_scan_range(ctx->dev, d_packed, n, w, r, static_cast<uint32_t*>(d_bitvec), d_count, st));
+    if (n == 0 || r.empty) {  // nothing can match: clear what a scan would have written
+        if (d_count && !accumulate) SSS_CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+        if (n != 0) SSS_CK(cudaMemsetAsync(d_bitvec, 0, 4 * ((n + 31) / 32), st));
+        return SSS_OK;
+    }
+    CountTarget ct{d_count, ctx->d_count_slots + 2 * (ctx->next_count_slot++ % kCountSlots), accumulate};
+    return cuda_status(launch_scan_range(ctx->dev, d_packed, n, w, r, static_cast<uint32_t*>(d_bitvec), ct, st));
 }
 
 int sss_scan_range(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32_t lo, uint32_t hi, void* d_bitvec,
@@ -269,7 +278,7 @@ int sss_scan_range(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32
     SSS_TRY(check_common(ctx, d_packed, w));
     if (d_bitvec == nullptr || (reinterpret_cast<uintptr_t>(d_bitvec) & 15)) return SSS_ERR_INVALID_ARG;
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
-    return scan_range_impl(ctx, d_packed, n, w, lo, hi, d_bitvec, reinterpret_cast<unsigned long long*>(d_count), true,
+    return scan_range_impl(ctx, d_packed, n, w, lo, hi, d_bitvec, reinterpret_cast<unsigned long long*>(d_count), false,
                            static_cast<cudaStream_t>(stream));
 }
 
@@ -388,7 +397,7 @@ int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, u
         SSS_TRY(grow(&s.d_out, &s.out_cap, C / 8));
         const uint8_t* src = static_cast<const uint8_t*>(h_packed) + first * (uint64_t)w / 8;
         SSS_CK(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
-        SSS_TRY(scan_range_impl(ctx, s.d_in, cnt, w, lo, hi, s.d_out, ctx->d_counts, false, s.stream));
+        SSS_TRY(scan_range_impl(ctx, s.d_in, cnt, w, lo, hi, s.d_out, ctx->d_counts, true, s.stream));
         const uint64_t out_off = first / 8;
         const uint64_t out_bytes = std::min<uint64_t>(4 * ((cnt + 31) / 32), out_total - out_off);
         SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_bitvec) + out_off, s.d_out, out_bytes, cudaMemcpyDeviceToHost,

@@ -271,4 +271,31 @@ __device__ __forceinline__ void cta_add_u64(uint32_t v, unsigned long long* glob
     }
 }
 
+// Count without a separate memset launch.  `slot` points at {accumulator, ticket}, both zero between
+// launches (a context-owned pool, see capi.cu).  Every CTA adds its sum to the accumulator and takes
+// a ticket; the CTA that draws the last ticket publishes the total to *result (stored, or added when
+// `accumulate`), and re-zeroes the slot for its next user.
+__device__ __forceinline__ void cta_finish_count(uint32_t v, unsigned long long* slot, unsigned long long* result,
+                                                 bool accumulate)
+{
+    __shared__ uint32_t warp_sums[kWarps];
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+#pragma unroll
+        for (int i = 0; i < kWarps; i++) s += warp_sums[i];
+        if (s) atomicAdd(&slot[0], s);
+        __threadfence();
+        const unsigned long long ticket = atomicAdd(&slot[1], 1ull);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            const unsigned long long total = atomicExch(&slot[0], 0ull);
+            slot[1] = 0;
+            if (accumulate) atomicAdd(result, total); else *result = total;
+        }
+    }
+}
+
 }  // namespace sss

@@ -16,9 +16,18 @@ struct Device {
     int smem_optin;  // max dynamic shared memory per CTA
 };
 
+// Where a kernel's match count goes: `result` (device, may be null = no count) is stored or added to by
+// the last CTA; `slot` = {accumulator, ticket}, zero between launches (context-owned pool), so no
+// memset launch is needed per scan.
+struct CountTarget {
+    unsigned long long* result;
+    unsigned long long* slot;
+    bool accumulate;
+};
+
 // scan.cu -- fused unpack + range compare -> bitvector (+count)
 cudaError_t launch_scan_range(const Device& dev, const void* packed, uint64_t n, int w, AlignedRange r,
-                              uint32_t* bitvec, unsigned long long* count, cudaStream_t stream);
+                              uint32_t* bitvec, const CountTarget& count, cudaStream_t stream);
 
 // unpack.cu -- packed -> int32 per code
 cudaError_t launch_unpack(const Device& dev, const void* packed, uint64_t n, int w, int32_t* out,

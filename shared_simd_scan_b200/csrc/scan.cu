@@ -185,7 +185,8 @@ template <int W, int kMode>
 __global__ void __launch_bounds__(kThreads, ScanPlan<W>::kCtasPerSm)
 scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                   const __grid_constant__ ScanArgs<W> args, uint32_t* __restrict__ bitvec,
-                  unsigned long long* __restrict__ count)
+                  unsigned long long* __restrict__ count, unsigned long long* __restrict__ count_slot,
+                  bool accumulate)
 {
     using P = ScanPlan<W>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -211,14 +212,14 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
         }
         ring.release(iter, tile);
     }
-    if (count != nullptr) cta_add_u64(hits, count);
+    if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
 }
 
 // ---- launch ---------------------------------------------------------------------------------------
 
 template <int W, int kMode>
 static cudaError_t launch_mode(const Device& dev, const void* packed, uint64_t n, const ScanArgs<W>& args,
-                               uint32_t* bitvec, unsigned long long* count, cudaStream_t stream)
+                               uint32_t* bitvec, const CountTarget& ct, cudaStream_t stream)
 {
     using P = ScanPlan<W>;
     constexpr int smem = P::Ring::kSmemBytes;
@@ -234,13 +235,14 @@ static cudaError_t launch_mode(const Device& dev, const void* packed, uint64_t n
     const uint64_t tiles = (readable + P::kTileBytes - 1) / P::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * P::kCtasPerSm;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    scan_range_kernel<W, kMode><<<grid, kThreads, smem, stream>>>(packed, readable, n, args, bitvec, count);
+    scan_range_kernel<W, kMode><<<grid, kThreads, smem, stream>>>(packed, readable, n, args, bitvec, ct.result, ct.slot,
+                                                                  ct.accumulate);
     return cudaGetLastError();
 }
 
 template <int W>
 static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, uint32_t lo, uint32_t hi,
-                            uint32_t* bitvec, unsigned long long* count, cudaStream_t stream)
+                            uint32_t* bitvec, const CountTarget& count, cudaStream_t stream)
 {
     // caller guarantees lo <= hi <= 2^W - 1 (non-empty range, already clamped)
     ScanArgs<W> args{};
@@ -261,7 +263,7 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, u
 }
 
 using ScanLauncher = cudaError_t (*)(const Device&, const void*, uint64_t, uint32_t, uint32_t, uint32_t*,
-                                     unsigned long long*, cudaStream_t);
+                                     const CountTarget&, cudaStream_t);
 
 template <int... Ws>
 static constexpr auto make_table(std::integer_sequence<int, Ws...>)
@@ -270,7 +272,7 @@ static constexpr auto make_table(std::integer_sequence<int, Ws...>)
 }
 
 cudaError_t launch_scan_range(const Device& dev, const void* packed, uint64_t n, int w, AlignedRange r,
-                              uint32_t* bitvec, unsigned long long* count, cudaStream_t stream)
+                              uint32_t* bitvec, const CountTarget& count, cudaStream_t stream)
 {
     static constexpr auto table = make_table(std::make_integer_sequence<int, 32>{});
     // recover the clamped code-domain bounds from the aligned form
