@@ -100,6 +100,22 @@ int sss_scan_range(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32
 int sss_positions(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base,
                   uint64_t* d_positions, uint64_t capacity, uint64_t* d_num, void* stream);
 
+/* Downstream consumers of a scan result (the reference stops at the bitvector).
+ * Combine two bitvectors over the first n bits: op = SSS_OP_AND / OR / ANDNOT (a & ~b) / XOR; writes
+ * 4*ceil(n/32) bytes with bits >= n cleared, *d_count (optional) = popcount of the result.  d_out may
+ * alias d_a or d_b. */
+#define SSS_OP_AND 0
+#define SSS_OP_OR 1
+#define SSS_OP_ANDNOT 2
+#define SSS_OP_XOR 3
+int sss_bitvec_combine(sss_ctx* ctx, int op, const void* d_a, const void* d_b, uint64_t n, void* d_out,
+                       uint64_t* d_count, void* stream);
+
+/* Late materialisation: d_out[i] = the code at d_positions[i] of a packed column (any order, any
+ * repeats; positions must be < the column's code count). */
+int sss_unpack_at(sss_ctx* ctx, const void* d_packed, int w, const uint64_t* d_positions, uint64_t num,
+                  int32_t* d_out, void* stream);
+
 /* shared_scan_* (src/simd_scan_shared.cpp:9-466): K bitvectors, predicate k's at
  * d_bitvecs + k*stride_bytes (stride a multiple of 4); d_counts[K] overwritten (may be NULL). */
 int sss_shared_scan(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo,

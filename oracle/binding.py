@@ -59,6 +59,10 @@ def lib() -> C.CDLL:
     L.orc_shared_scan_linear.restype = None
     L.orc_shared_scan_linear.argtypes = [C.c_void_p, sz, C.c_int, C.c_void_p, C.c_void_p, sz, C.c_int,
                                          C.c_void_p, C.c_void_p]
+    L.orc_bitvec_combine.restype = C.c_uint64
+    L.orc_bitvec_combine.argtypes = [C.c_int, C.c_void_p, C.c_void_p, sz, C.c_void_p]
+    L.orc_unpack_at.restype = None
+    L.orc_unpack_at.argtypes = [C.c_void_p, C.c_int, C.c_void_p, sz, C.c_void_p]
     L.orc_mix64.restype = C.c_uint64
     L.orc_mix64.argtypes = [C.c_uint64]
     L.orc_generate_codes.restype = None
@@ -140,6 +144,23 @@ def shared_scan_linear(packed: np.ndarray, n: int, w: int, lo, hi, granule: int 
     counts = np.zeros(K, dtype=np.uint64)
     lib().orc_shared_scan_linear(_ptr(packed), n, w, _ptr(lo), _ptr(hi), K, granule, _ptr(out), _ptr(counts))
     return out, counts
+
+
+COMBINE = {"and": 0, "or": 1, "andnot": 2, "xor": 3}
+
+
+def bitvec_combine(op: str, a: np.ndarray, b: np.ndarray, n: int):
+    out = np.zeros(4 * ((n + 31) // 32), dtype=np.uint8)
+    hits = lib().orc_bitvec_combine(COMBINE[op], _ptr(np.ascontiguousarray(a)), _ptr(np.ascontiguousarray(b)), n,
+                                    _ptr(out))
+    return out, int(hits)
+
+
+def unpack_at(packed: np.ndarray, w: int, positions) -> np.ndarray:
+    positions = np.ascontiguousarray(positions, dtype=np.uint64)
+    out = np.empty(len(positions), dtype=np.int32)
+    lib().orc_unpack_at(_ptr(packed), w, _ptr(positions), len(positions), _ptr(out))
+    return out
 
 
 def time_scan_range(packed: np.ndarray, n: int, w: int, lo: int, hi: int, threads: int, reps: int):

@@ -143,6 +143,32 @@ void orc_shared_scan_linear(const uint8_t* packed, size_t n, int w, const uint32
     }
 }
 
+uint64_t orc_bitvec_combine(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out)
+{
+    uint64_t hits = 0;
+    size_t words = (n + 31) / 32;
+    memset(out, 0, words * 4);
+    for (size_t i = 0; i < n; i++) {
+        int x = (a[i >> 3] >> (i & 7)) & 1, y = (b[i >> 3] >> (i & 7)) & 1, r;
+        switch (op) {
+            case 0: r = x & y; break;
+            case 1: r = x | y; break;
+            case 2: r = x & !y; break;
+            default: r = x ^ y; break;
+        }
+        if (r) {
+            out[i >> 3] |= (uint8_t)(1u << (i & 7));
+            hits++;
+        }
+    }
+    return hits;
+}
+
+void orc_unpack_at(const uint8_t* packed, int w, const uint64_t* positions, size_t num, int32_t* out)
+{
+    for (size_t i = 0; i < num; i++) out[i] = (int32_t)orc_code_at(packed, (size_t)positions[i], w);
+}
+
 /* SplitMix64 finaliser (public-domain constant set); SURVEY.md section 8d synthetic inputs. */
 uint64_t orc_mix64(uint64_t x)
 {

@@ -198,6 +198,34 @@ def shared_scan_linear(packed: torch.Tensor, n: int, w: int, lo, hi=None, out: O
     return out, counts
 
 
+_OPS = {"and": 0, "or": 1, "andnot": 2, "xor": 3}
+
+
+def bitvec_combine(op: str, a: torch.Tensor, b: torch.Tensor, n: int, out: Optional[torch.Tensor] = None,
+                   count: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """a OP b over the first n bits (op in and / or / andnot / xor) -> (bitvector, popcount int64[1])."""
+    ctx = Context.current()
+    if out is None:
+        out = torch.empty(bitvec_bytes(n), dtype=torch.uint8, device=a.device)
+    if count is None:
+        count = torch.empty(1, dtype=torch.int64, device=a.device)
+    check(lib().sss_bitvec_combine(ctx.handle, _OPS[op], a.data_ptr(), b.data_ptr(), n, out.data_ptr(),
+                                   count.data_ptr(), _stream()), "sss_bitvec_combine")
+    return out, count
+
+
+def decompress_at(packed: torch.Tensor, w: int, positions: torch.Tensor, num: Optional[int] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Late materialisation: the codes of a packed column at a position list (int64 / uint64 CUDA tensor)."""
+    ctx = Context.current()
+    num = positions.numel() if num is None else num
+    if out is None:
+        out = torch.empty(max(num, 1), dtype=torch.int32, device=packed.device)
+    check(lib().sss_unpack_at(ctx.handle, packed.data_ptr(), w, positions.data_ptr(), num, out.data_ptr(), _stream()),
+          "sss_unpack_at")
+    return out[:num]
+
+
 # ---- host-buffer operators (numpy arrays or pinned CPU tensors) ------------------------------------
 
 Host = Union[np.ndarray, torch.Tensor]

@@ -303,6 +303,36 @@ int sss_positions(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base,
 // One shared scan = build the predicate index, run the scan (which fills the index's interval
 // histogram), turn the histogram into per-predicate counts.  The index lives in the context, so a
 // context serves one shared scan at a time (calls on one stream serialise naturally).
+int sss_bitvec_combine(sss_ctx* ctx, int op, const void* d_a, const void* d_b, uint64_t n, void* d_out,
+                       uint64_t* d_count, void* stream)
+{
+    if (ctx == nullptr || d_a == nullptr || d_b == nullptr || d_out == nullptr) return SSS_ERR_INVALID_ARG;
+    if (op < SSS_OP_AND || op > SSS_OP_XOR) return SSS_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_a) | reinterpret_cast<uintptr_t>(d_b) | reinterpret_cast<uintptr_t>(d_out)) & 15)
+        return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    auto st = static_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        if (d_count) SSS_CK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+        return SSS_OK;
+    }
+    CountTarget ct{reinterpret_cast<unsigned long long*>(d_count),
+                   ctx->d_count_slots + 2 * (ctx->next_count_slot++ % kCountSlots), false};
+    return cuda_status(launch_bitvec_combine(ctx->dev, op, static_cast<const uint32_t*>(d_a),
+                                             static_cast<const uint32_t*>(d_b), n, static_cast<uint32_t*>(d_out), ct, st));
+}
+
+int sss_unpack_at(sss_ctx* ctx, const void* d_packed, int w, const uint64_t* d_positions, uint64_t num, int32_t* d_out,
+                  void* stream)
+{
+    SSS_TRY(check_common(ctx, d_packed, w));
+    if (num != 0 && (d_positions == nullptr || d_out == nullptr)) return SSS_ERR_INVALID_ARG;
+    if (num == 0) return SSS_OK;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    return cuda_status(launch_unpack_at(ctx->dev, d_packed, w, reinterpret_cast<const unsigned long long*>(d_positions),
+                                        num, d_out, static_cast<cudaStream_t>(stream)));
+}
+
 static int shared_scan_body(sss_ctx* ctx, bool linear, const void* d_packed, uint64_t n, int w, int K, void* d_out,
                             uint64_t stride_bytes, bool count_matches, cudaStream_t st)
 {

@@ -53,6 +53,12 @@ cudaError_t launch_pack(const Device& dev, const uint32_t* codes, uint64_t n, in
 cudaError_t launch_generate_packed(const Device& dev, uint32_t* packed, uint64_t packed_words, uint64_t n, int w,
                                    uint64_t seed, uint64_t first_index, cudaStream_t stream);
 
+// consumers.cu -- what a column store does next with a scan result
+cudaError_t launch_bitvec_combine(const Device& dev, int op, const uint32_t* a, const uint32_t* b, uint64_t n,
+                                  uint32_t* out, const CountTarget& count, cudaStream_t stream);
+cudaError_t launch_unpack_at(const Device& dev, const void* packed, int w, const unsigned long long* positions,
+                             uint64_t num, int32_t* out, cudaStream_t stream);
+
 // positions.cu -- bitvector -> ascending position list
 size_t positions_workspace_bytes(uint64_t n);
 cudaError_t launch_positions(const Device& dev, const uint32_t* bitvec, uint64_t n, uint64_t base,

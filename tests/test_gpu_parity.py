@@ -366,3 +366,35 @@ def test_c_abi_argument_errors(sss):
     assert L.sss_scan_range(ctx, buf.data_ptr(), 0, 9, 1, 2, out.data_ptr(), cnt.data_ptr(), None) == 0
     torch.cuda.synchronize()
     assert int(cnt.item()) == 0 and not out.any()
+
+
+@pytest.mark.parametrize("op", ["and", "or", "andnot", "xor"])
+def test_bitvec_combine(sss, op):
+    for n in [1, 37, 128, 100_003, (1 << 22) + 5]:
+        w = 12
+        codes, packed = column(n, w, seed=700 + n % 97)
+        d = dev(packed)
+        a, _ = sss.scan(d, n, w, 100, 3000)
+        b, _ = sss.scan(d, n, w, 2000, 4095)
+        out, cnt = sss.bitvec_combine(op, a, b, n)
+        exp, ehits = B.bitvec_combine(op, host(a), host(b), n)
+        assert (host(out)[: len(exp)] == exp).all() and int(cnt.item()) == ehits, (op, n)
+        # in place
+        a2 = a.clone()
+        sss.bitvec_combine(op, a2, b, n, out=a2)
+        assert torch.equal(a2[: len(exp)], out[: len(exp)])
+
+
+@pytest.mark.parametrize("w", [1, 9, 17, 32])
+def test_late_materialisation(sss, w):
+    """scan one column -> position list -> fetch the matching rows of ANOTHER packed column."""
+    n = 200_003
+    codes_a, packed_a = column(n, 11, seed=801)
+    codes_b, packed_b = column(n, w, seed=802 + w)
+    bv, cnt = sss.scan(dev(packed_a), n, 11, 17, 300)
+    pos, num = sss.positions(bv, n)
+    k = int(num.item())
+    got = host(sss.decompress_at(dev(packed_b), w, pos, num=k))
+    exp = B.unpack_at(packed_b, w, host(pos)[:k].astype(np.uint64))
+    assert (got == exp).all()
+    assert (got.astype(np.uint32) == codes_b[(codes_a >= 17) & (codes_a <= 300)]).all()
