@@ -38,7 +38,7 @@ struct ScanPlan {
     static constexpr bool kSwar = (W >= 2 && W <= 12);
     static constexpr bool kRot = (W == 8 || W == 16 || W == 32);
     // 128-bit shared-memory loads (group of kG blocks per thread, kG*W a multiple of 4 words)
-    static constexpr bool kVec = (W == 1) || kRot || (kSwar && W != 9 && W != 11);
+    static constexpr bool kVec = (W == 1) || kRot || (kSwar && W != 11);
     static constexpr int kG = !kVec ? 1 : (W == 1 ? 4 : (W % 4 == 0 ? 1 : (W % 2 == 0 ? 2 : 4)));
     static constexpr int kGroupWords = kG * W;
 #ifndef SSS_SCAN_TILE_WORDS
