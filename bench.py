@@ -29,6 +29,14 @@ import sys
 import threading
 import time
 
+_json_out = sys.stdout
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the contract, on the process's original stdout (see main())."""
+    _json_out.write(json.dumps(line) + "\n")
+    _json_out.flush()
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -229,7 +237,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "codes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -299,13 +307,13 @@ def run_cfg5(args):
     peak, _ = measured_peak()
     bytes_per_gpu = shard.count * (w / 8 + K / 8)
     if rank == 0:
-        print(json.dumps({
+        emit({
             "workload": f"cfg5: shared scan K=64 over {world} x 2^{args.cfg5_logn} 23-bit codes, range-sharded, "
                         "NCCL all-reduce of the 64 counts", "n_gpus": world, "steps": args.steps, "ms_per_step": ms,
             "value": world * shard.count / (ms * 1e-3), "unit": "codes/s", "scaling": "weak",
             "per_gpu_gb_per_s": round(bytes_per_gpu / ms / 1e6, 1),
             "per_gpu_frac_of_measured_peak": round(bytes_per_gpu / ms / 1e6 / peak, 4),
-            "global_count_of_query_0": int(counts[0].item())}), flush=True)
+            "global_count_of_query_0": int(counts[0].item())})
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -461,7 +469,7 @@ def run_ours(args):
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -558,6 +566,13 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner,
+    # compiler chatter) is sent to stderr instead, and the line is written to the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    global _json_out
+    _json_out = os.fdopen(saved, "w")
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.workload == "cfg5":
