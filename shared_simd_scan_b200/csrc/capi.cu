@@ -333,25 +333,44 @@ int sss_unpack_at(sss_ctx* ctx, const void* d_packed, int w, const uint64_t* d_p
                                         num, d_out, static_cast<cudaStream_t>(stream)));
 }
 
+// true when the scan kernel itself adds the match counts to `d_counts` (no histogram epilogue)
+static bool counts_directly(bool, int K) { return K <= kDirectCountMaxK; }
+
+// One predicate: the shared scan IS the single-predicate scan (one bitvector, one count; the linear
+// layout of K = 1 is the bitvector too), run with its bounds read from device memory.  No index.
+static int single_predicate_body(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo,
+                                 const uint32_t* d_hi, void* d_out, unsigned long long* d_count, bool accumulate,
+                                 cudaStream_t st)
+{
+    if (n == 0) {
+        if (d_count && !accumulate) SSS_CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+        return SSS_OK;
+    }
+    CountTarget ct{d_count, ctx->d_count_slots + 2 * (ctx->next_count_slot++ % kCountSlots), accumulate};
+    return cuda_status(launch_scan_range_dev(ctx->dev, d_packed, n, w, d_lo, d_hi, static_cast<uint32_t*>(d_out), ct, st));
+}
+
 static int shared_scan_body(sss_ctx* ctx, bool linear, const void* d_packed, uint64_t n, int w, int K, void* d_out,
-                            uint64_t stride_bytes, bool count_matches, cudaStream_t st)
+                            uint64_t stride_bytes, unsigned long long* d_counts, cudaStream_t st)
 {
     if (n == 0) return SSS_OK;
     if (linear)
         return cuda_status(launch_shared_scan_linear(ctx->dev, d_packed, n, w, ctx->d_index, K,
-                                                     static_cast<uint8_t*>(d_out), count_matches, st));
+                                                     static_cast<uint8_t*>(d_out), d_counts, d_counts != nullptr, st));
     return cuda_status(launch_shared_scan(ctx->dev, d_packed, n, w, ctx->d_index, K, static_cast<uint32_t*>(d_out),
-                                          stride_bytes / 4, count_matches, st));
+                                          stride_bytes / 4, d_counts, d_counts != nullptr, st));
 }
 
 static int shared_impl(sss_ctx* ctx, bool linear, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo,
                        const uint32_t* d_hi, int K, void* d_out, uint64_t stride_bytes, unsigned long long* d_counts,
                        cudaStream_t st)
 {
+    if (K == 1 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0)  // (the scan kernel stores 128-bit pieces)
+        return single_predicate_body(ctx, d_packed, n, w, d_lo, d_hi, d_out, d_counts, false, st);
     if (d_counts) SSS_CK(cudaMemsetAsync(d_counts, 0, (size_t)K * sizeof(unsigned long long), st));
     SSS_CK(launch_build_pred_index(d_lo, d_hi, K, w, ctx->d_index, st));
-    SSS_TRY(shared_scan_body(ctx, linear, d_packed, n, w, K, d_out, stride_bytes, d_counts != nullptr, st));
-    if (d_counts) SSS_CK(launch_counts_from_histogram(ctx->d_index, K, d_counts, st));
+    SSS_TRY(shared_scan_body(ctx, linear, d_packed, n, w, K, d_out, stride_bytes, d_counts, st));
+    if (d_counts && !counts_directly(linear, K)) SSS_CK(launch_counts_from_histogram(ctx->d_index, K, d_counts, st));
     return SSS_OK;
 }
 
@@ -457,7 +476,8 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
     SSS_CK(cudaMemcpyAsync(ctx->d_lo, h_lo, (size_t)K * 4, cudaMemcpyHostToDevice, s0));
     SSS_CK(cudaMemcpyAsync(ctx->d_hi, h_hi, (size_t)K * 4, cudaMemcpyHostToDevice, s0));
     SSS_CK(cudaMemsetAsync(ctx->d_counts, 0, (size_t)K * sizeof(unsigned long long), s0));
-    SSS_CK(launch_build_pred_index(ctx->d_lo, ctx->d_hi, K, w, ctx->d_index, s0));
+    const bool single = K == 1;  // see single_predicate_body
+    if (!single) SSS_CK(launch_build_pred_index(ctx->d_lo, ctx->d_hi, K, w, ctx->d_index, s0));
     SSS_CK(cudaStreamSynchronize(s0));
     int slot = 0;
     for (uint64_t first = 0; first < n_eval; first += C, slot = (slot + 1) % kSlots) {
@@ -469,7 +489,12 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
         const uint8_t* src = static_cast<const uint8_t*>(h_packed) + first * (uint64_t)w / 8;
         SSS_CK(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
         const uint64_t chunk_stride = C / 8;  // device-side bitvector stride inside the slot
-        SSS_TRY(shared_scan_body(ctx, linear, s.d_in, cnt, w, K, s.d_out, chunk_stride, h_counts != nullptr, s.stream));
+        if (single)
+            SSS_TRY(single_predicate_body(ctx, s.d_in, cnt, w, ctx->d_lo, ctx->d_hi, s.d_out,
+                                          h_counts != nullptr ? ctx->d_counts : nullptr, true, s.stream));
+        else
+            SSS_TRY(shared_scan_body(ctx, linear, s.d_in, cnt, w, K, s.d_out, chunk_stride,
+                                     h_counts != nullptr ? ctx->d_counts : nullptr, s.stream));
         const uint64_t out_off = first / 8;  // bytes per predicate / rows already produced
         const uint64_t piece = std::min<uint64_t>(4 * ((cnt + 31) / 32), out_total - out_off);
         if (linear) {
@@ -487,7 +512,8 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
     }
     for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
     if (h_counts) {
-        SSS_CK(launch_counts_from_histogram(ctx->d_index, K, ctx->d_counts, s0));
+        if (!single && !counts_directly(linear, K))
+            SSS_CK(launch_counts_from_histogram(ctx->d_index, K, ctx->d_counts, s0));
         SSS_CK(cudaMemcpyAsync(h_counts, ctx->d_counts, (size_t)K * sizeof(uint64_t), cudaMemcpyDeviceToHost, s0));
         SSS_CK(cudaStreamSynchronize(s0));
     }

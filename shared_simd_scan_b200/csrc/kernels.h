@@ -29,6 +29,10 @@ struct CountTarget {
 cudaError_t launch_scan_range(const Device& dev, const void* packed, uint64_t n, int w, AlignedRange r,
                               uint32_t* bitvec, const CountTarget& count, cudaStream_t stream);
 
+// the same scan with lo/hi in device memory (one-predicate shared scans); an empty range writes zeros
+cudaError_t launch_scan_range_dev(const Device& dev, const void* packed, uint64_t n, int w, const uint32_t* d_lo,
+                                  const uint32_t* d_hi, uint32_t* bitvec, const CountTarget& count, cudaStream_t stream);
+
 // unpack.cu -- packed -> int32 per code
 cudaError_t launch_unpack(const Device& dev, const void* packed, uint64_t n, int w, int32_t* out,
                           cudaStream_t stream);
@@ -39,13 +43,18 @@ cudaError_t launch_build_pred_index(const uint32_t* d_lo, const uint32_t* d_hi, 
                                     cudaStream_t stream);
 cudaError_t launch_counts_from_histogram(void* d_index, int K, unsigned long long* d_counts, cudaStream_t stream);
 
-// shared.cu -- K predicates in one pass -> K bitvectors; match counts go to the index's histogram
+// shared.cu -- K predicates in one pass -> K bitvectors.  Match counts: for K <= kDirectCountMaxK the
+// kernel ADDS them to counts[0..K) itself; above they go to the index's interval histogram and
+// launch_counts_from_histogram finishes the job.
+constexpr int kDirectCountMaxK = 8;
 cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n, int w, const void* index, int K,
-                               uint32_t* bitvecs, uint64_t stride_words, bool count_matches, cudaStream_t stream);
+                               uint32_t* bitvecs, uint64_t stride_words, unsigned long long* counts, bool count_matches,
+                               cudaStream_t stream);
 
 // linear.cu -- K predicates in one pass -> [4*ceil(n/32)][K] byte matrix
 cudaError_t launch_shared_scan_linear(const Device& dev, const void* packed, uint64_t n, int w, const void* index,
-                                      int K, uint8_t* out, bool count_matches, cudaStream_t stream);
+                                      int K, uint8_t* out, unsigned long long* counts, bool count_matches,
+                                      cudaStream_t stream);
 
 // pack.cu -- compressor and synthetic-column generator
 cudaError_t launch_pack(const Device& dev, const uint32_t* codes, uint64_t n, int w, uint32_t* packed,

@@ -24,11 +24,9 @@
 
 namespace sss {
 
-// Threads per CTA of the index-driven kernels.  They are latency-bound (dependent shared-memory
-// lookups), so more resident warps help: 2 CTAs x 320 threads = 20 warps/SM within the register file
-// at <= 102 registers per thread.
+// Threads per CTA of the index-driven kernels: one 512-thread CTA per SM (see shared.cu).
 #ifndef SSS_SHARED_THREADS
-#define SSS_SHARED_THREADS 256
+#define SSS_SHARED_THREADS 512
 #endif
 constexpr int kSThreads = SSS_SHARED_THREADS;
 
@@ -36,13 +34,14 @@ template <int W>
 struct LinearCfg {
     static constexpr int kBlocksPerTile = kSThreads;
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
-    // compute-bound kernels: a shallow ring is enough and leaves shared memory for the mask table
-    static constexpr int kStages = kTileBytes >= 16 * 1024 ? 2 : 3;
+    // compute-bound kernels: a shallow ring is enough and leaves shared memory for the row table
+    static constexpr int kStages = kTileBytes >= 32 * 1024 ? 2 : 3;
     using Ring = TileRing<kTileBytes, kStages>;
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
 };
 
-constexpr int kLinCounterBytes = (kMaxBp + 1 + 3) / 4 * 16;
+// more than this many predicates: one warp per block (shared_scan_linear_wide_kernel)
+constexpr int kLinearWideMinK = 16 * 32;
 
 // in : a[8i + e] byte p bit f  = predicate 8p+f on code 8i+e           (i = row, e = code in group)
 // out: a[8i + 4*f2 + p] byte (f & 3) bit e, f2 = f >> 2                 = row i, bytes 8p+4*f2 .. +3
@@ -83,19 +82,66 @@ __device__ __forceinline__ void store_row_piece(uint8_t* dst, const uint32_t (&w
 {
     if (vec32 && kk >= 32) {
         st_v8_u32(dst, ws);
-    } else if (vec16 && kk >= 32) {
+        return;
+    }
+    int q0 = 0;
+    if (vec16 && kk >= 16) {
         __stcs(reinterpret_cast<uint4*>(dst), make_uint4(ws[0], ws[1], ws[2], ws[3]));
-        __stcs(reinterpret_cast<uint4*>(dst) + 1, make_uint4(ws[4], ws[5], ws[6], ws[7]));
+        q0 = 4;
+        if (kk >= 32) {
+            __stcs(reinterpret_cast<uint4*>(dst) + 1, make_uint4(ws[4], ws[5], ws[6], ws[7]));
+            return;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (q < q0) continue;
+        if (4 * q + 4 <= kk && vec4) {
+            __stcs(reinterpret_cast<uint32_t*>(dst) + q, ws[q]);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (4 * q + b < kk) dst[4 * q + b] = (uint8_t)(ws[q] >> (8 * b));
+        }
+    }
+}
+
+// 4 x 4 byte transpose: in a,b,c,d = four predicates' result words (byte g = codes 8g..8g+7);
+// out o[g] = bytes (a.g, b.g, c.g, d.g) = four consecutive predicate bytes of row g
+__device__ __forceinline__ void byte_transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t (&o)[4])
+{
+    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(c, d, 0x5140);
+    const uint32_t t2 = __byte_perm(a, b, 0x7362), t3 = __byte_perm(c, d, 0x7362);
+    o[0] = __byte_perm(t0, t1, 0x5410);
+    o[1] = __byte_perm(t0, t1, 0x7632);
+    o[2] = __byte_perm(t2, t3, 0x5410);
+    o[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+// The 4 rows x K bytes of a block for K <= 8, from the per-predicate result words r[k] (bit j = code j):
+// the rows of a block are contiguous (4K bytes), so K = 1, 2, 4, 8 are ONE 4/8/16/32-byte store.
+__device__ __forceinline__ void store_block_small(uint8_t* dst, const uint32_t (&r)[8], int K)
+{
+    uint32_t lo[4], hi[4];
+    byte_transpose4(r[0], r[1], r[2], r[3], lo);
+    if (K == 1 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+        __stcs(reinterpret_cast<uint32_t*>(dst), r[0]);
+    } else if (K == 2 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+        __stcs(reinterpret_cast<uint2*>(dst),
+               make_uint2(__byte_perm(lo[0], lo[1], 0x5410), __byte_perm(lo[2], lo[3], 0x5410)));
+    } else if (K == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        __stcs(reinterpret_cast<uint4*>(dst), make_uint4(lo[0], lo[1], lo[2], lo[3]));
     } else {
+        byte_transpose4(r[4], r[5], r[6], r[7], hi);
+        if (K == 8 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+            const uint32_t ws[8] = {lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], lo[3], hi[3]};
+            st_v8_u32(dst, ws);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            if (4 * q + 4 <= kk && vec4) {
-                __stcs(reinterpret_cast<uint32_t*>(dst) + q, ws[q]);
-            } else {
+            for (int g = 0; g < 4; g++)
 #pragma unroll
-                for (int b = 0; b < 4; b++)
-                    if (4 * q + b < kk) dst[4 * q + b] = (uint8_t)(ws[q] >> (8 * b));
-            }
+                for (int k = 0; k < 8; k++)
+                    if (k < K) dst[g * K + k] = (uint8_t)((k < 4 ? lo[g] : hi[g]) >> (8 * (k & 3)));
         }
     }
 }
@@ -111,9 +157,9 @@ __device__ __forceinline__ uint32_t code_id_runtime(const uint32_t* blk, uint32_
     } else {
         const uint32_t t = v << (32 - W);
         const uint32_t e = static_cast<const uint32_t*>(ix.locator)[t >> (32 - kBucketBits)];
-        uint32_t id = (e >> (kThrBits + 1)) + ((t << kBucketBits) > (e << kBucketBits) ? 1u : 0u);
+        uint32_t id = (e & kBucketIdMask) + ((t << kBucketBits) > e ? 1u : 0u);
         if (e & kSeveralBit) {
-            uint32_t i = e >> (kThrBits + 1);
+            uint32_t i = e & kBucketIdMask;
             while (t > ix.thr[i]) i++;
             id = i;
         }
@@ -130,16 +176,15 @@ __device__ __forceinline__ uint32_t code_id_runtime(const uint32_t* blk, uint32_
 // network and owns bytes 32c..32c+31 of the block's four output rows -- so a warp writes each row as
 // one contiguous run of K bytes.
 template <int W, bool kSmem>
-__global__ void __launch_bounds__(kSThreads, 2)
+__global__ void __launch_bounds__(kSThreads, 1)
 shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                                const uint8_t* __restrict__ g_index, int K, uint8_t* __restrict__ out,
-                               bool count_matches)
+                               bool count_matches, const IndexSmemPlan plan)
 {
     using Cfg = LinearCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);
-    for (int i = threadIdx.x; i < 2 * K + 1; i += kSThreads) s_hist[i] = 0;
-    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kLinCounterBytes, kSmem);
+    const IntervalHist hist = hist_init(smem + Cfg::kRingBytes, plan);
+    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + plan.hist_bytes, plan);
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();
 
@@ -147,6 +192,7 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const int cols = (K + 31) >> 5;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rows_base = kSmem ? ix.rows_saddr : 0u;
     const bool vec32 = (K & 31) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0;
     const bool vec16 = (K & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const bool vec4 = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
@@ -165,12 +211,12 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
             const uint32_t valid = (tail_bits != 0 && gb == n_blocks - 1) ? tail_bits : 32u;
             const uint32_t id = code_id_runtime<W>(buf + blk * W, lane, ix);
             dep |= id;
-            if (count_matches && lane < valid) atomicAdd(&s_hist[id], 1u);
+            if (count_matches && lane < valid) hist.add(id);
             uint32_t m[32];
-            const uint32_t row_off = id * ix.row_words * 4;  // my code's mask row, in bytes
+            const uint32_t row_off = id * ix.row_bytes + rows_base;  // my code's mask row
 #pragma unroll
             for (int j = 0; j < 32; j++)
-                m[j] = mask_word_at<kSmem>(ix, __shfl_sync(0xFFFFFFFFu, row_off, j), 4 * my_col);
+                m[j] = row_mask_word<kSmem>(ix, __shfl_sync(0xFFFFFFFFu, row_off, j), 4 * my_col);
             if (valid != 32) {  // only the column's last block: codes past n contribute zero bits
 #pragma unroll
                 for (int j = 0; j < 32; j++)
@@ -190,34 +236,33 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
         ring.release_warp(iter, tile, dep);
     }
     __syncthreads();
-    if (count_matches) {
-        unsigned long long* g_hist =
-            reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(g_index) + PredIndexLayout::kHist);
-        for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += kSThreads)
-            if (s_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)s_hist[i]);
-    }
+    if (count_matches) hist_flush(smem + Cfg::kRingBytes, plan, ix.num_bp, g_index);
 }
 
 template <int W, bool kSmem>
-__global__ void __launch_bounds__(kSThreads, 2)
+__global__ void __launch_bounds__(kSThreads, 1)
 shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
-                          const uint8_t* __restrict__ g_index, int K, uint8_t* __restrict__ out, bool count_matches)
+                          const uint8_t* __restrict__ g_index, int K, uint8_t* __restrict__ out,
+                          unsigned long long* __restrict__ counts, bool count_matches, const IndexSmemPlan plan)
 {
     using Cfg = LinearCfg<W>;
+    using Rot = BlockRot<W, 8>;  // rotations by whole rows (8 codes) only
     extern __shared__ __align__(128) uint8_t smem[];
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);  // per-CTA interval histogram
-    for (int i = threadIdx.x; i < 2 * K + 1; i += kSThreads) s_hist[i] = 0;
-    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kLinCounterBytes, kSmem);
+    uint8_t* s_index = smem + Cfg::kRingBytes + plan.hist_bytes;
+    const IntervalHist hist = hist_init(smem + Cfg::kRingBytes, plan);  // kSmem: empty, the rows carry the counters
+    const PredIndexView ix = load_pred_index(g_index, s_index, plan);
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();
 
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const int cols = (K + 31) >> 5;
+    const uint32_t lane_rot = Rot::lane_rot();
     // widest store the row pitch K and the base alignment allow
     const bool vec32 = (K & 31) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0;
     const bool vec16 = (K & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const bool vec4 = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+    uint32_t direct[kDirectCountMaxK] = {};  // K <= 8: this thread's match counts
 
     uint32_t iter = 0;
     for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
@@ -225,35 +270,65 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
         const bool active = gb < n_blocks;
+        const bool last = tail_bits != 0 && gb == n_blocks - 1;  // the one ragged block of the column
+        // register j holds code (j + rot * kPieceCodes) mod 32; the ragged block is read unrotated
+        const uint32_t rot = last ? 0u : lane_rot;
         uint32_t x[W];
-#pragma unroll
-        for (int k = 0; k < W; k++) x[k] = active ? buf[threadIdx.x * W + k] : 0u;
+        load_block<W, 8>(buf, threadIdx.x, x, rot);
         uint32_t loaded = 0;
 #pragma unroll
         for (int k = 0; k < W; k++) loaded |= x[k];
         ring.release_warp(iter, tile, loaded);  // the stage is free once every warp has copied its words
         if (active) {
-            const bool last = tail_bits != 0 && gb == n_blocks - 1;  // the one ragged block of the column
             uint32_t id[32];
             block_ids<W>(x, ix, id);
-            if (count_matches) {
+            uint8_t* row0 = out + gb * 4 * (uint64_t)K;  // rows 4*gb .. 4*gb+3
+            if (K <= kDirectCountMaxK) {
+                // per-predicate result words as in shared.cu, then bytes -> rows
+                rows_of_ids<kSmem>(ix, id);
+                uint32_t m[32], r[8];
+#pragma unroll
+                for (int j = 0; j < 32; j++) m[j] = row_mask_word<kSmem>(ix, id[j], 0);  // (no counter column)
+                transpose32x8(m, r);
+                const uint32_t keep = last ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if constexpr (Rot::kRot) r[k] = __funnelshift_l(r[k], r[k], rot * Rot::kPieceCodes);
+                    r[k] &= keep;
+                    if (k < K) direct[k] += __popc(r[k]);
+                }
+                store_block_small(row0, r, K);
+                continue;
+            }
+            if (!kSmem && count_matches) {  // separate histogram, indexed by the interval id
                 if (!last) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) atomicAdd(&s_hist[id[j]], 1u);
+                    for (int j = 0; j < 32; j++) hist.add(id[j]);
                 } else {
-                    for (uint32_t j = 0; j < tail_bits; j++) {
-                        uint32_t v = 0;
 #pragma unroll
-                        for (int q = 0; q < 32; q++) v = (q == (int)j) ? id[q] : v;
-                        atomicAdd(&s_hist[v], 1u);
-                    }
+                    for (int j = 0; j < 32; j++)
+                        if ((uint32_t)j < tail_bits) hist.add(id[j]);
                 }
             }
-            uint8_t* row0 = out + gb * 4 * (uint64_t)K;  // rows 4*gb .. 4*gb+3
+            rows_of_ids<kSmem>(ix, id);
+            if (kSmem && count_matches) {  // the rows carry their interval's counter
+                if (!last) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) row_count(id[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if ((uint32_t)j < tail_bits) row_count(id[j]);
+                }
+            }
+            const uint32_t row_rot = rot * (Rot::kPieceCodes / 8);  // register row i is output row (i + row_rot) & 3
             for (int c = 0; c < cols; c++) {
                 uint32_t m[32];
+                // derived from the kernel parameter so that it stays in a uniform register: LDS [R + UR]
+                const uint32_t col_bytes =
+                    kSmem ? (((uint32_t)c + plan.has_counter) << (plan.rep_log2 + 2)) : (uint32_t)c * 4u;
 #pragma unroll
-                for (int j = 0; j < 32; j++) m[j] = mask_word<kSmem>(ix, id[j], c);
+                for (int j = 0; j < 32; j++) m[j] = row_mask_word<kSmem>(ix, id[j], col_bytes);
                 if (last) {  // codes past n contribute zero bits
 #pragma unroll
                     for (int j = 0; j < 32; j++)
@@ -263,7 +338,8 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
                 const int kk = K - 32 * c;  // predicates in this column
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    uint8_t* dst = row0 + (uint64_t)i * K + 32 * c;
+                    const uint32_t orow = Rot::kRot ? ((i + row_rot) & 3u) : (uint32_t)i;
+                    uint8_t* dst = row0 + (uint64_t)orow * K + 32 * c;
                     // word q of the row = m[8i + 4*(q&1) + (q>>1)]
                     const uint32_t ws[8] = {m[8 * i + 0], m[8 * i + 4], m[8 * i + 1], m[8 * i + 5],
                                             m[8 * i + 2], m[8 * i + 6], m[8 * i + 3], m[8 * i + 7]};
@@ -274,31 +350,33 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
     }
     __syncthreads();
     if (count_matches) {
-        unsigned long long* g_hist =
-            reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(g_index) + PredIndexLayout::kHist);
-        for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += kSThreads)
-            if (s_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)s_hist[i]);
+        if (K <= kDirectCountMaxK) {
+#pragma unroll
+            for (int k = 0; k < kDirectCountMaxK; k++) {
+                const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, direct[k]);
+                if ((threadIdx.x & 31) == 0 && k < K && s != 0) atomicAdd(&counts[k], (unsigned long long)s);
+            }
+        } else if (kSmem) {
+            merged_hist_flush(ix, plan, s_index, g_index);
+        } else {
+            hist_flush(smem + Cfg::kRingBytes, plan, ix.num_bp, g_index);
+        }
     }
 }
 
 template <int W, bool kSmem>
 static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, const void* index, int K, uint8_t* out,
-                             bool count_matches, size_t smem, cudaStream_t stream)
+                             unsigned long long* counts, bool count_matches, const IndexSmemPlan& plan,
+                             cudaStream_t stream)
 {
     using Cfg = LinearCfg<W>;
-    static size_t configured[64] = {};
-    if (configured[dev.ordinal & 63] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(shared_scan_linear_kernel<W, kSmem>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured[dev.ordinal & 63] = smem;
-    }
+    const size_t smem = Cfg::kRingBytes + plan.total_bytes;
     const uint64_t n_blocks = (n + 31) / 32;
     const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
-    const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
+    const uint64_t max_ctas = (uint64_t)dev.sm_count;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    if (K > 16 * 32) {
+    if (K > kLinearWideMinK) {
         static size_t configured_wide[64] = {};
         if (configured_wide[dev.ordinal & 63] < smem) {
             cudaError_t e = cudaFuncSetAttribute(shared_scan_linear_wide_kernel<W, kSmem>,
@@ -307,27 +385,36 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
             configured_wide[dev.ordinal & 63] = smem;
         }
         shared_scan_linear_wide_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(
-            packed, readable, n, static_cast<const uint8_t*>(index), K, out, count_matches);
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, count_matches, plan);
         return cudaGetLastError();
     }
+    static size_t configured[64] = {};
+    if (configured[dev.ordinal & 63] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(shared_scan_linear_kernel<W, kSmem>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev.ordinal & 63] = smem;
+    }
     shared_scan_linear_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(
-        packed, readable, n, static_cast<const uint8_t*>(index), K, out, count_matches);
+        packed, readable, n, static_cast<const uint8_t*>(index), K, out, counts, count_matches, plan);
     return cudaGetLastError();
 }
 
 template <int W>
 static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K, uint8_t* out,
-                            bool count_matches, cudaStream_t stream)
+                            unsigned long long* counts, bool count_matches, cudaStream_t stream)
 {
-    bool masks_in_smem = false;
-    const size_t other = LinearCfg<W>::kRingBytes + kLinCounterBytes;
-    const size_t smem = other + pred_index_smem_bytes(K, W, other, &masks_in_smem) + 64;
-    if (masks_in_smem) return launch_ws<W, true>(dev, packed, n, index, K, out, count_matches, smem, stream);
-    return launch_ws<W, false>(dev, packed, n, index, K, out, count_matches, smem, stream);
+    // the wide kernel reads mask rows lane-contiguously (conflict-free already): no mask replicas
+    const bool wide = K > kLinearWideMinK;
+    const IndexSmemPlan plan = plan_index_smem(K, W, LinearCfg<W>::kRingBytes, /*use_hist=*/K > kDirectCountMaxK,
+                                               /*merged_ok=*/!wide);
+    if (plan.masks_in_smem)
+        return launch_ws<W, true>(dev, packed, n, index, K, out, counts, count_matches, plan, stream);
+    return launch_ws<W, false>(dev, packed, n, index, K, out, counts, count_matches, plan, stream);
 }
 
-using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, uint8_t*, bool,
-                                 cudaStream_t);
+using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, uint8_t*,
+                                 unsigned long long*, bool, cudaStream_t);
 
 template <int... Ws>
 static constexpr auto make_table(std::integer_sequence<int, Ws...>)
@@ -336,10 +423,11 @@ static constexpr auto make_table(std::integer_sequence<int, Ws...>)
 }
 
 cudaError_t launch_shared_scan_linear(const Device& dev, const void* packed, uint64_t n, int w, const void* index,
-                                      int K, uint8_t* out, bool count_matches, cudaStream_t stream)
+                                      int K, uint8_t* out, unsigned long long* counts, bool count_matches,
+                                      cudaStream_t stream)
 {
     static constexpr auto table = make_table(std::make_integer_sequence<int, 32>{});
-    return table[w - 1](dev, packed, n, index, K, out, count_matches, stream);
+    return table[w - 1](dev, packed, n, index, K, out, counts, count_matches, stream);
 }
 
 }  // namespace sss

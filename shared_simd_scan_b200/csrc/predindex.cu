@@ -4,7 +4,7 @@
 //   2. bitonic sort of the (<= 2048) breakpoints in shared memory, 64-bit keys (2^32 = "none")
 //   3. compaction of the distinct values (block prefix sum)
 //   4. mask rows: row i, predicate k  <-  lo_k <= start_i <= hi_k   (fill_masks_kernel, many CTAs)
-//   5. locator: direct lut (W <= 13) or 4096 buckets on the top 12 bits
+//   5. locator: direct lut (W <= 13) or 8192 buckets on the top 13 bits
 #include <algorithm>
 
 #include "predindex.cuh"
@@ -139,7 +139,7 @@ build_pred_index_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restr
             const uint32_t inner = count_le(bp, M, end) - base;  // start < breakpoint <= end
             // threshold on the bits below the bucket bits of the LEFT-aligned code
             const uint32_t thr = inner ? (((bp[base] << (32 - w)) & kThrMask) - 1u) : kThrMask;
-            bucket[b] = (base << (kThrBits + 1)) | (inner >= 2 ? kSeveralBit : 0u) | thr;
+            bucket[b] = make_bucket_word(base, inner >= 2, thr);
         }
     }
 }

@@ -14,7 +14,7 @@
 //   mask rows    mask[id][k] = 1  iff  lo_k <= start(id) <= hi_k   ceil(K/32) words per row
 //   locator      W <= 13 : lut[v] = id(v) * row_bytes             (direct, 2 bytes per code value)
 //                W  > 13 : 8192 buckets on the top 13 bits of the code, ONE 32-bit word each:
-//                          [id at bucket start : 12][several breakpoints inside : 1][threshold : 19];
+//                          [threshold : 19][several breakpoints inside : 1][id at bucket start : 12];
 //                          a bucket with at most one inner breakpoint resolves with one compare of the
 //                          code's remaining bits against the threshold, the rare others re-search
 //
@@ -31,7 +31,7 @@ constexpr int kMaxBp = 2 * kMaxK;      // breakpoints
 constexpr int kDirectMaxW = 13;        // direct locator up to 2^13 code values
 constexpr int kBucketBits = 13;
 constexpr int kBuckets = 1 << kBucketBits;
-constexpr int kSharedSmemBudget = 112 * 1024;  // per CTA, two CTAs per SM: the mask table lives in shared
+constexpr int kSharedSmemBudget = 224 * 1024;  // per CTA, ONE 512-thread CTA per SM: the mask table lives in shared
                                                // memory whenever ring + counters + index fit in this
 
 struct PredIndexHeader {
@@ -77,43 +77,100 @@ cudaError_t launch_counts_from_histogram(void* d_index, int K, unsigned long lon
 struct PredIndexView {
     const uint32_t* thr;      // shared
     const void* locator;      // shared
-    const uint32_t* masks;    // shared or global
-    uint32_t masks_saddr;     // shared-window address of the mask table (when it lives in shared memory)
-    uint32_t row_words;
+    const uint32_t* masks;    // global table (kSmem = false)
+    uint32_t rows_saddr;      // shared-window address of this lane's replica of row 0 (kSmem = true)
+    uint32_t row_bytes;       // bytes between the rows of consecutive intervals
+    uint32_t col_bytes;       // bytes between consecutive 32-predicate columns of one row
+    uint32_t mask0_bytes;     // offset of mask column 0 inside a row (merged rows with a counter: col_bytes)
     uint32_t num_bp;
     bool direct;
 };
 
-// shared-memory bytes the kernels need for the index of this launch; `other_bytes` is what the
-// kernel already uses (tile ring + interval counters)
-inline size_t pred_index_smem_bytes(int K, int w, size_t other_bytes, bool* masks_in_smem)
+// ---- shared-memory plan of an index-driven launch ----------------------------------------------------
+//
+// Per CTA, after the tile ring:  [separate histogram][locator][thresholds][row table].
+//
+// The lookups of a warp go to 32 unrelated addresses, so on average ~3 of them fall into the same
+// bank (ncu, K = 64: 2.9 wavefronts per LDS, 2.8 per ATOMS).  Shared memory that is left over is
+// therefore spent on LANE-PRIVATE REPLICAS of the small per-interval tables: with R = 2^r copies
+// interleaved word by word, lane l uses copy l mod R; at R = 32 every lane stays in its own bank
+// and every access is a single wavefront.
+//
+//   merged rows (thread-per-block kernels, table fits):
+//       row[id] = [match counter][mask column 0][mask column 1]..., each R words; one multiply-add
+//       turns an interval id into the address of its row = of its counter, the mask columns are at
+//       warp-uniform offsets from it.  Row stride in R-word groups is made odd while R < 32.
+//   separate (wide linear kernel; tables too large): histogram hist[id][R_h] in front, masks as the
+//       flat global layout (row stride = ceil(K/32) made odd), in shared memory if they fit.
+struct IndexSmemPlan {
+    uint32_t merged;          // 1: merged rows, 0: separate histogram
+    uint32_t rep_log2;        // merged: replicas of the row table
+    uint32_t row_groups;      // merged: row stride in R-word groups
+    uint32_t has_counter;     // merged: group 0 of every row is the interval's match counter
+    uint32_t masks_in_smem;
+    uint32_t hist_rep_log2;   // separate: replicas of the histogram
+    uint32_t hist_bytes;      // separate: bytes of the histogram in front of the index (0: none)
+    uint32_t total_bytes;     // everything after the ring
+};
+
+inline IndexSmemPlan plan_index_smem(int K, int w, size_t ring_bytes, bool use_hist, bool merged_ok)
 {
-    const size_t stride = pred_row_stride_words(K);
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    IndexSmemPlan p{};
+    const size_t cols = ((size_t)K + 31) / 32;
     const size_t max_rows = (w >= 31) ? (size_t)(2 * K + 1) : std::min<size_t>((size_t)2 * K + 1, (size_t)1 << w);
-    const size_t mask_bytes = (max_rows * stride * 4 + 15) & ~(size_t)15;
     const size_t locator = (w <= kDirectMaxW) ? ((size_t)2 << w) : (size_t)kBuckets * 4;
     const size_t thr = (w <= kDirectMaxW) ? 0 : (std::min<size_t>(2 * (size_t)K, kMaxBp) + 1) * 4;
-    const size_t base = ((locator + 15) & ~(size_t)15) + ((thr + 15) & ~(size_t)15);
-    *masks_in_smem = other_bytes + base + mask_bytes + 64 <= (size_t)kSharedSmemBudget;
-    return base + (*masks_in_smem ? mask_bytes : 0);
+    const size_t index = up16(locator) + up16(thr) + 64;
+    const size_t budget = (size_t)kSharedSmemBudget;
+    if (merged_ok) {
+        const size_t groups0 = cols + (use_hist ? 1 : 0);
+        for (int r = 5; r >= 0; r--) {
+            const size_t groups = (r == 5) ? groups0 : (groups0 | 1);
+            const size_t bytes = up16((max_rows * groups * 4) << r);
+            if (ring_bytes + index + bytes <= budget) {
+                p.merged = 1;
+                p.masks_in_smem = 1;
+                p.rep_log2 = (uint32_t)r;
+                p.row_groups = (uint32_t)groups;
+                p.has_counter = use_hist ? 1u : 0u;
+                p.total_bytes = (uint32_t)(index + bytes);
+                return p;
+            }
+        }
+    }
+    auto hist_bytes = [&](uint32_t r) { return use_hist ? up16((max_rows * 4) << r) : (size_t)0; };
+    const size_t flat = up16(max_rows * (cols | 1) * 4);
+    // (a kernel that asked for merged rows and did not get them reads its masks from global memory)
+    p.masks_in_smem = (!merged_ok && ring_bytes + index + hist_bytes(0) + flat <= budget) ? 1u : 0u;
+    const size_t masks = p.masks_in_smem ? flat : 0;
+    // masks read from global memory go through L1, which shares the SM's 256 KB with shared memory:
+    // keep the footprint small then
+    const size_t hist_cap = p.masks_in_smem ? 32 * 1024 : 8 * 1024 + 64;
+    while (use_hist && p.hist_rep_log2 < 5 && hist_bytes(p.hist_rep_log2 + 1) <= hist_cap &&
+           ring_bytes + index + hist_bytes(p.hist_rep_log2 + 1) + masks <= budget)
+        p.hist_rep_log2++;
+    p.hist_bytes = (uint32_t)hist_bytes(p.hist_rep_log2);
+    p.total_bytes = (uint32_t)(p.hist_bytes + index + masks);
+    return p;
 }
 
-// All threads: copy the index into shared memory at `smem` (16-byte aligned).  Visible after the
-// next __syncthreads.
+// All threads: copy the index into shared memory at `smem` (16-byte aligned; behind the separate
+// histogram if there is one), expanding the mask table into the plan's layout and zeroing the
+// merged counters.  Visible after the next __syncthreads.
 __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restrict__ g_index, uint8_t* smem,
-                                                         bool masks_in_smem)
+                                                         const IndexSmemPlan& plan)
 {
     const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(g_index + PredIndexLayout::kHeader);
     PredIndexView v;
     v.num_bp = h->num_bp;
-    v.row_words = h->row_words;
     v.direct = h->direct != 0;
+    const uint32_t g_row_words = h->row_words;
     const uint32_t locator_bytes = v.direct ? (2u << h->w) : (uint32_t)kBuckets * 4;
     const uint32_t thr_bytes = v.direct ? 0u : (v.num_bp + 1) * 4;  // + the 0xFFFFFFFF sentinel
-    const uint32_t mask_bytes = (v.num_bp + 1) * v.row_words * 4;
     uint8_t* s_loc = smem;
     uint8_t* s_thr = s_loc + ((locator_bytes + 15) & ~15u);
-    uint8_t* s_mask = s_thr + ((thr_bytes + 15) & ~15u);
+    uint8_t* s_rows = s_thr + ((thr_bytes + 15) & ~15u);
     auto copy = [&](uint8_t* dst, const uint8_t* src, uint32_t bytes) {
         const uint32_t n16 = (bytes + 15) / 16;
         for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x)
@@ -123,15 +180,156 @@ __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restri
     copy(s_thr, g_index + PredIndexLayout::kThr, thr_bytes);
     v.locator = s_loc;
     v.thr = reinterpret_cast<const uint32_t*>(s_thr);
-    if (masks_in_smem) {
-        copy(s_mask, g_index + PredIndexLayout::kMasks, mask_bytes);
-        v.masks = reinterpret_cast<const uint32_t*>(s_mask);
-        v.masks_saddr = smem_u32(s_mask);
+    const uint32_t* g_masks = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kMasks);
+    v.masks = g_masks;
+    v.mask0_bytes = 0;
+    if (plan.merged) {
+        // thread -> (row, group, replica); consecutive threads write consecutive words
+        const uint32_t r = plan.rep_log2, R = 1u << r;
+        const uint32_t cols = (h->K + 31) / 32, groups = plan.row_groups, first = plan.has_counter;
+        const uint32_t total = ((v.num_bp + 1) * groups) << r;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_rows);
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const uint32_t cell = i >> r, row = cell / groups, c = cell - row * groups - first;  // c: mask column
+            dst[i] = c < cols ? __ldg(g_masks + row * g_row_words + c) : 0u;  // (counter and padding: zero)
+        }
+        v.rows_saddr = smem_u32(s_rows) + ((threadIdx.x & (R - 1)) << 2);
+        v.row_bytes = (groups << r) * 4;
+        v.col_bytes = 4u << r;
+        v.mask0_bytes = plan.has_counter * v.col_bytes;
+    } else if (plan.masks_in_smem) {
+        copy(s_rows, g_index + PredIndexLayout::kMasks, (v.num_bp + 1) * g_row_words * 4);
+        v.rows_saddr = smem_u32(s_rows);
+        v.row_bytes = g_row_words * 4;
+        v.col_bytes = 4;
     } else {
-        v.masks_saddr = 0;
-        v.masks = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kMasks);
+        v.rows_saddr = 0;
+        v.row_bytes = g_row_words * 4;
+        v.col_bytes = 4;
     }
     return v;
+}
+
+// merged rows: add the counters of this CTA (summed over the replicas) to the index's global histogram.
+// All threads, after the __syncthreads that follows the last count.
+__device__ __forceinline__ void merged_hist_flush(const PredIndexView& ix, const IndexSmemPlan& plan, uint8_t* s_index,
+                                                  const uint8_t* g_index)
+{
+    const uint32_t R = 1u << plan.rep_log2;
+    // recompute the table base the way load_pred_index laid it out
+    const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(g_index + PredIndexLayout::kHeader);
+    const uint32_t locator_bytes = ix.direct ? (2u << h->w) : (uint32_t)kBuckets * 4;
+    const uint32_t thr_bytes = ix.direct ? 0u : (ix.num_bp + 1) * 4;
+    const uint32_t* rows =
+        reinterpret_cast<const uint32_t*>(s_index + ((locator_bytes + 15) & ~15u) + ((thr_bytes + 15) & ~15u));
+    unsigned long long* g_hist =
+        reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(g_index) + PredIndexLayout::kHist);
+    for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += blockDim.x) {
+        const uint32_t* c = rows + (((size_t)i * plan.row_groups) << plan.rep_log2);
+        uint32_t s = 0;
+        for (uint32_t r = 0; r < R; r++) s += c[(r + i) & (R - 1)];  // rotated start: no bank conflicts
+        if (s) atomicAdd(&g_hist[i], (unsigned long long)s);
+    }
+}
+
+// The separate interval histogram of a CTA: `rep_log2` lane-private replicas per interval.
+struct IntervalHist {
+    uint32_t* mine;   // this lane's replica of interval 0
+    uint32_t shift;   // log2(replicas)
+    __device__ __forceinline__ void add(uint32_t id) const { atomicAdd(mine + (id << shift), 1u); }
+};
+
+// All threads, before the __syncthreads that precedes the first add()
+__device__ __forceinline__ IntervalHist hist_init(uint8_t* smem, const IndexSmemPlan& plan)
+{
+    uint32_t* h = reinterpret_cast<uint32_t*>(smem);
+    const uint32_t words = plan.hist_bytes / 4;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) h[i] = 0;
+    const uint32_t R = 1u << plan.hist_rep_log2;
+    return IntervalHist{h + (threadIdx.x & (R - 1)), plan.hist_rep_log2};
+}
+
+// All threads, after the __syncthreads that follows the last add(): fold the replicas and add the
+// CTA's interval counts to the global histogram of the index
+__device__ __forceinline__ void hist_flush(const uint8_t* smem, const IndexSmemPlan& plan, uint32_t num_bp,
+                                           const uint8_t* g_index)
+{
+    const uint32_t* h = reinterpret_cast<const uint32_t*>(smem);
+    const uint32_t R = 1u << plan.hist_rep_log2;
+    unsigned long long* g_hist =
+        reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(g_index) + PredIndexLayout::kHist);
+    for (uint32_t i = threadIdx.x; i <= num_bp; i += blockDim.x) {
+        uint32_t s = 0;
+        for (uint32_t r = 0; r < R; r++) s += h[(i << plan.hist_rep_log2) + ((r + i) & (R - 1))];
+        if (s) atomicAdd(&g_hist[i], (unsigned long long)s);
+    }
+}
+
+// ---- one 32-code block: shared memory -> registers ------------------------------------------------
+//
+// A thread owns a whole block (W consecutive words of the tile), so the 32 lanes of a warp read with
+// a stride of W words.  That is conflict-free only for odd W.  Widest conflict-free access per width:
+//   odd W          32-bit loads, stride W (odd)
+//   W = 2 mod 4    64-bit loads, stride W/2 (odd) -- a half-warp per wavefront
+//   W = 4 mod 8    128-bit loads, stride W/4 (odd) -- a quarter-warp per wavefront
+//   W = 0 mod 8    128-bit loads with a lane-dependent ROTATION: the block is cut into kPieces equal
+//                  pieces of whole 16-byte chunks that hold whole codes (8/16/32 bit: one chunk,
+//                  24 bit: three chunks = 16 codes) and lane l starts at piece rot(l), so that the
+//                  eight lanes of a quarter-warp touch eight different bank groups.  Register j then
+//                  holds code (j + rot * kPieceCodes) mod 32 of the block; callers undo that on the
+//                  RESULT (one funnel shift per result word, or a permutation of the output rows).
+// kGranule: the rotation has to be a multiple of this many codes (1: bitvector words, 8: the linear
+// layout's rows of 8 codes; 32-bit codes then rotate by two chunks and keep a 2-way conflict).
+template <int W, int kGranule>
+struct BlockRot {
+    static constexpr int kChunks = W / 4;
+    static constexpr int kBaseChunks = (W == 24) ? 3 : 1;
+    static constexpr int kBaseCodes = (W % 8 == 0) ? kBaseChunks * 128 / W : 32;
+    static constexpr int kMul = kBaseCodes >= kGranule ? 1 : kGranule / kBaseCodes;
+    static constexpr int kPieceChunks = kBaseChunks * kMul;
+    static constexpr int kPieces = (W % 8 == 0) ? kChunks / kPieceChunks : 1;
+    static constexpr int kPieceCodes = 32 / kPieces;
+    static constexpr bool kRot = kPieces > 1;
+    // lanes l and l + 8/g start in the same bank group (g = gcd(kChunks, 8)): spread them over the pieces
+    static constexpr int kGcd = (kChunks % 8 == 0) ? 8 : (kChunks % 4 == 0 ? 4 : (kChunks % 2 == 0 ? 2 : 1));
+    static __device__ __forceinline__ uint32_t lane_rot()
+    {
+        if constexpr (!kRot) return 0u;
+        return (((threadIdx.x & 31u) * kGcd) >> 3) & (uint32_t)(kPieces - 1);
+    }
+};
+
+template <int W, int kGranule>
+__device__ __forceinline__ void load_block(const uint32_t* buf, uint32_t blk, uint32_t (&x)[W], uint32_t rot)
+{
+    using R = BlockRot<W, kGranule>;
+    if constexpr (W % 4 == 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(buf) + (size_t)blk * R::kChunks;
+#pragma unroll
+        for (int q = 0; q < R::kChunks; q++) {
+            uint32_t c = q;
+            if constexpr (R::kRot) {
+                c = q + rot * R::kPieceChunks;
+                c = c >= (uint32_t)R::kChunks ? c - R::kChunks : c;
+            }
+            const uint4 v = src[c];
+            x[4 * q + 0] = v.x;
+            x[4 * q + 1] = v.y;
+            x[4 * q + 2] = v.z;
+            x[4 * q + 3] = v.w;
+        }
+    } else if constexpr (W % 2 == 0) {
+        const uint2* src = reinterpret_cast<const uint2*>(buf) + (size_t)blk * (W / 2);
+#pragma unroll
+        for (int q = 0; q < W / 2; q++) {
+            const uint2 v = src[q];
+            x[2 * q + 0] = v.x;
+            x[2 * q + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; k++) x[k] = buf[(size_t)blk * W + k];
+    }
 }
 
 // ---- interval ids of the 32 codes of a block ---------------------------------------------------
@@ -139,15 +337,23 @@ __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restri
 // id(code) = number of breakpoints <= code, from the LEFT-aligned code t (garbage allowed in the
 // low 32-W bits).  Branch-free for all 32 codes so that the 32 locator loads overlap.
 //
-// Bucket word e = id_at_bucket_start << 20 | several << 19 | thr19.  The bucket fixes the top 13
-// bits of t, so only the remaining 19 decide:  t >= breakpoint  <=>  (t << 13) > (e << 13)  with
-// thr19 = (left-aligned breakpoint & 0x7FFFF) - 1, and thr19 = 0x7FFFF (never exceeded) for a bucket
-// without an inner breakpoint.  Buckets with two or more inner breakpoints (K = 64: ~0.01 % of the
-// codes of a uniform column; every equality predicate, whose breakpoints key and key+1 are
+// Bucket word e = thr19 << 13 | several << 12 | id_at_bucket_start.  The bucket fixes the top 13 bits
+// of t, so only the remaining 19 decide:  t >= breakpoint  <=>  (t << 13) > e  with
+// thr19 = (left-aligned breakpoint & 0x7FFFF) - 1 (the low 13 bits of t << 13 are zero, so whatever
+// sits below thr19 in e cannot turn a tie into "greater"), and thr19 = 0x7FFFF (never exceeded) for a
+// bucket without an inner breakpoint.  Buckets with two or more inner breakpoints (K = 64: ~0.01 % of
+// the codes of a uniform column; every equality predicate, whose breakpoints key and key+1 are
 // adjacent) set `several`; a block that met one patches the ids of exactly those codes (fix()).
 constexpr int kThrBits = 32 - kBucketBits;           // 19
 constexpr uint32_t kThrMask = (1u << kThrBits) - 1;  // 0x7FFFF
-constexpr uint32_t kSeveralBit = 1u << kThrBits;
+constexpr uint32_t kBucketIdMask = (1u << (kBucketBits - 1)) - 1;  // 12 bits: ids 0..2048
+constexpr uint32_t kSeveralBit = 1u << (kBucketBits - 1);
+static_assert(kMaxBp <= (int)kBucketIdMask, "interval ids must fit below the several flag");
+
+SSS_HD inline uint32_t make_bucket_word(uint32_t id_at_start, bool several, uint32_t thr19)
+{
+    return (thr19 << kBucketBits) | (several ? kSeveralBit : 0u) | id_at_start;
+}
 
 template <int W, int J>
 struct BlockIds {
@@ -159,7 +365,7 @@ struct BlockIds {
             id[J] = static_cast<const uint16_t*>(ix.locator)[t >> (32 - W)];
         } else {
             const uint32_t e = static_cast<const uint32_t*>(ix.locator)[t >> (32 - kBucketBits)];
-            id[J] = (e >> (kThrBits + 1)) + ((t << kBucketBits) > (e << kBucketBits) ? 1u : 0u);
+            id[J] = (e & kBucketIdMask) + ((t << kBucketBits) > e ? 1u : 0u);
             flags |= e;
         }
         BlockIds<W, J + 1>::fast(x, ix, id, flags);
@@ -172,7 +378,7 @@ struct BlockIds {
             const uint32_t t = left_aligned_code<W, J>(x);
             const uint32_t e = static_cast<const uint32_t*>(ix.locator)[t >> (32 - kBucketBits)];
             if (e & kSeveralBit) {
-                uint32_t i = e >> (kThrBits + 1);
+                uint32_t i = e & kBucketIdMask;
                 while (t > ix.thr[i]) i++;
                 id[J] = i;
             }
@@ -194,34 +400,33 @@ __device__ __forceinline__ void block_ids(const uint32_t (&x)[W], const PredInde
     if (flags & kSeveralBit) BlockIds<W, 0>::fix(x, ix, id);
 }
 
-// word c of the mask row of interval `id`; kSmem selects shared-memory addressing (LDS) over the
-// generic path used when the table is too large for shared memory (K > 128 or so)
+// interval ids -> row handles: the shared-window address of the lane's replica of the row (kSmem),
+// or the row's byte offset in the global table.  One multiply-add per code; the mask columns and the
+// match counter are then at warp-uniform offsets.
 template <bool kSmem>
-__device__ __forceinline__ uint32_t mask_word(const PredIndexView& ix, uint32_t id, int c)
+__device__ __forceinline__ void rows_of_ids(const PredIndexView& ix, uint32_t (&id)[32])
 {
-    const uint32_t word = id * ix.row_words + (uint32_t)c;
+#pragma unroll
+    for (int j = 0; j < 32; j++) id[j] = id[j] * ix.row_bytes + (kSmem ? ix.rows_saddr : 0u);
+}
+
+// mask word of a row handle at column byte offset `col_bytes` (warp-uniform)
+template <bool kSmem>
+__device__ __forceinline__ uint32_t row_mask_word(const PredIndexView& ix, uint32_t row, uint32_t col_bytes)
+{
     if constexpr (kSmem) {
         uint32_t v;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ix.masks_saddr + word * 4));
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(row + col_bytes));
         return v;
     } else {
-        return __ldg(ix.masks + word);
+        return __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(ix.masks) + row + col_bytes));
     }
 }
 
-// Same with the row already resolved to a byte offset (id * row_words * 4) and the column to bytes:
-// lets a caller hoist the multiply out of its inner loop.
-template <bool kSmem>
-__device__ __forceinline__ uint32_t mask_word_at(const PredIndexView& ix, uint32_t row_byte_offset, uint32_t col_bytes)
+// merged rows: count one code of this row's interval (lane-private counter: no conflicts at R = 32)
+__device__ __forceinline__ void row_count(uint32_t row)
 {
-    if constexpr (kSmem) {
-        uint32_t v;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ix.masks_saddr + row_byte_offset + col_bytes));
-        return v;
-    } else {
-        return __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(ix.masks) + row_byte_offset +
-                                                       col_bytes));
-    }
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(row) : "memory");
 }
 
 // ---- 32 x 32 bit-matrix transpose in registers ------------------------------------------------------

@@ -181,18 +181,12 @@ __device__ __forceinline__ uint32_t scan_tile(const uint32_t* buf, const ScanArg
     return hits;
 }
 
+// every tile this CTA owns (static round-robin); returns the thread's match count
 template <int W, int kMode>
-__global__ void __launch_bounds__(kThreads, ScanPlan<W>::kCtasPerSm)
-scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
-                  const __grid_constant__ ScanArgs<W> args, uint32_t* __restrict__ bitvec,
-                  unsigned long long* __restrict__ count, unsigned long long* __restrict__ count_slot,
-                  bool accumulate)
+__device__ __forceinline__ uint32_t scan_tiles(typename ScanPlan<W>::Ring& ring, const ScanArgs<W>& args, uint64_t n,
+                                               uint32_t* __restrict__ bitvec)
 {
     using P = ScanPlan<W>;
-    extern __shared__ __align__(128) uint8_t smem[];
-    typename P::Ring ring(smem, packed, readable_bytes16);
-    ring.start();
-
     const uint64_t n_blocks = (n + 31) >> 5;  // result words
     const uint64_t full_blocks = n >> 5;      // blocks whose 32 codes are all valid
     const uint32_t tail_bits = (uint32_t)(n & 31);
@@ -211,6 +205,65 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
             hits += scan_tile<W, kMode, true>(buf, args, rot, tile_out, n_blocks - tile_block0, tail_bits);
         }
         ring.release(iter, tile);
+    }
+    return hits;
+}
+
+template <int W, int kMode>
+__global__ void __launch_bounds__(kThreads, ScanPlan<W>::kCtasPerSm)
+scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
+                  const __grid_constant__ ScanArgs<W> args, uint32_t* __restrict__ bitvec,
+                  unsigned long long* __restrict__ count, unsigned long long* __restrict__ count_slot,
+                  bool accumulate)
+{
+    using P = ScanPlan<W>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    typename P::Ring ring(smem, packed, readable_bytes16);
+    ring.start();
+    const uint32_t hits = scan_tiles<W, kMode>(ring, args, n, bitvec);
+    if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
+}
+
+// The same scan with its bounds in DEVICE memory: a shared scan with a single predicate is this
+// kernel (one bitvector, one count -- for K = 1 the linear layout is the bitvector too), and the
+// shared-scan entry points take their bounds as device arrays.  The per-launch constants that
+// launch_w() prepares on the host are built here by every thread (a few hundred instructions once
+// per thread, against thousands of blocks scanned); an invalid or empty predicate writes zeros.
+template <int W>
+__global__ void __launch_bounds__(kThreads, ScanPlan<W>::kCtasPerSm)
+scan_range_dev_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
+                      const uint32_t* __restrict__ d_lo, const uint32_t* __restrict__ d_hi,
+                      uint32_t* __restrict__ bitvec, unsigned long long* __restrict__ count,
+                      unsigned long long* __restrict__ count_slot, bool accumulate)
+{
+    using P = ScanPlan<W>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t lo = __ldg(d_lo);
+    uint32_t hi = __ldg(d_hi);
+    uint32_t hits = 0;
+    if (lo > hi || lo > code_mask(W)) {  // matches nothing (kernel-uniform)
+        const uint64_t n_blocks = (n + 31) >> 5;
+        for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n_blocks; i += (uint64_t)gridDim.x * kThreads)
+            bitvec[i] = 0u;
+    } else {
+        if (hi > code_mask(W)) hi = code_mask(W);
+        typename P::Ring ring(smem, packed, readable_bytes16);
+        ring.start();
+        ScanArgs<W> args{};
+        if constexpr (W == 1) {
+            args.onebit.flip = (lo == 0 && hi == 0) ? 0xFFFFFFFFu : 0u;
+            args.onebit.all = (lo == 0 && hi == 1) ? 0xFFFFFFFFu : 0u;
+            hits = scan_tiles<W, kOneBit>(ring, args, n, bitvec);
+        } else if constexpr (P::kSwar) {
+            args.swar = make_swar_consts<W>(lo, hi);
+            hits = args.swar.lo_top ? scan_tiles<W, kSwarLoTop1>(ring, args, n, bitvec)
+                                    : scan_tiles<W, kSwarLoTop0>(ring, args, n, bitvec);
+        } else {
+            const AlignedRange r = aligned_range(W, lo, hi);
+            args.scalar.lo_al = r.lo_al;
+            args.scalar.span_al = r.span_al;
+            hits = scan_tiles<W, kScalar>(ring, args, n, bitvec);
+        }
     }
     if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
 }
@@ -262,13 +315,42 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, u
     }
 }
 
+template <int W>
+static cudaError_t launch_w_dev(const Device& dev, const void* packed, uint64_t n, const uint32_t* d_lo,
+                                const uint32_t* d_hi, uint32_t* bitvec, const CountTarget& ct, cudaStream_t stream)
+{
+    using P = ScanPlan<W>;
+    constexpr int smem = P::Ring::kSmemBytes;
+    static bool configured[64] = {};
+    if (!configured[dev.ordinal & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(scan_range_dev_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured[dev.ordinal & 63] = true;
+    }
+    const uint64_t n_blocks = (n + 31) / 32;
+    const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
+    const uint64_t tiles = (readable + P::kTileBytes - 1) / P::kTileBytes;
+    const uint64_t max_ctas = (uint64_t)dev.sm_count * P::kCtasPerSm;
+    const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
+    scan_range_dev_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, d_lo, d_hi, bitvec, ct.result,
+                                                               ct.slot, ct.accumulate);
+    return cudaGetLastError();
+}
+
 using ScanLauncher = cudaError_t (*)(const Device&, const void*, uint64_t, uint32_t, uint32_t, uint32_t*,
                                      const CountTarget&, cudaStream_t);
+using ScanDevLauncher = cudaError_t (*)(const Device&, const void*, uint64_t, const uint32_t*, const uint32_t*,
+                                        uint32_t*, const CountTarget&, cudaStream_t);
 
 template <int... Ws>
 static constexpr auto make_table(std::integer_sequence<int, Ws...>)
 {
     return std::array<ScanLauncher, sizeof...(Ws)>{&launch_w<Ws + 1>...};
+}
+template <int... Ws>
+static constexpr auto make_dev_table(std::integer_sequence<int, Ws...>)
+{
+    return std::array<ScanDevLauncher, sizeof...(Ws)>{&launch_w_dev<Ws + 1>...};
 }
 
 cudaError_t launch_scan_range(const Device& dev, const void* packed, uint64_t n, int w, AlignedRange r,
@@ -280,6 +362,13 @@ cudaError_t launch_scan_range(const Device& dev, const void* packed, uint64_t n,
     const uint32_t lo = r.lo_al >> s;
     const uint32_t hi = (r.lo_al + r.span_al) >> s;
     return table[w - 1](dev, packed, n, lo, hi, bitvec, count, stream);
+}
+
+cudaError_t launch_scan_range_dev(const Device& dev, const void* packed, uint64_t n, int w, const uint32_t* d_lo,
+                                  const uint32_t* d_hi, uint32_t* bitvec, const CountTarget& count, cudaStream_t stream)
+{
+    static constexpr auto table = make_dev_table(std::make_integer_sequence<int, 32>{});
+    return table[w - 1](dev, packed, n, d_lo, d_hi, bitvec, count, stream);
 }
 
 }  // namespace sss

@@ -22,11 +22,11 @@
 
 namespace sss {
 
-// Threads per CTA of the index-driven kernels.  They are latency-bound (dependent shared-memory
-// lookups), so more resident warps help: 2 CTAs x 320 threads = 20 warps/SM within the register file
-// at <= 102 registers per thread.
+// Threads per CTA of the index-driven kernels: ONE 512-thread CTA per SM.  The kernels are bound by
+// instruction issue and shared-memory wavefronts, not by occupancy, and a single CTA per SM keeps
+// one copy of the locator (32 KB) and leaves room for 32 lane-private replicas of the row table.
 #ifndef SSS_SHARED_THREADS
-#define SSS_SHARED_THREADS 256
+#define SSS_SHARED_THREADS 512
 #endif
 constexpr int kSThreads = SSS_SHARED_THREADS;
 
@@ -34,33 +34,39 @@ template <int W>
 struct SharedCfg {
     static constexpr int kBlocksPerTile = kSThreads;  // one 32-code block per thread per tile
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
-    // compute-bound kernels: a shallow ring is enough and leaves shared memory for the mask table
-    static constexpr int kStages = kTileBytes >= 16 * 1024 ? 2 : 3;
+    // compute-bound kernels: a shallow ring is enough and leaves shared memory for the row table
+    static constexpr int kStages = kTileBytes >= 32 * 1024 ? 2 : 3;
     using Ring = TileRing<kTileBytes, kStages>;
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
 };
 
-constexpr int kCounterBytes = (kMaxBp + 1 + 3) / 4 * 16;  // up to 2K+1 uint32 interval counters, 16-byte multiple
+// Up to kDirectCountMaxK predicates the kernel counts matches by popcounting its result words
+// (K/32 instructions per code) and adds them straight to the caller's counters; above, counting goes
+// through the interval histogram (one shared-memory atomic per code, independent of K).
+static_assert(kDirectCountMaxK == 8, "the K <= 8 path of shared_scan_kernel is the direct-count path");
 
-// kSmem: the mask table fits in shared memory (otherwise it is read through L1 from global memory)
+// kSmem: merged row table in shared memory (otherwise the masks are read through L1 from global
+// memory and the interval histogram is a separate shared-memory array)
 template <int W, bool kSmem>
-__global__ void __launch_bounds__(kSThreads, 2)
+__global__ void __launch_bounds__(kSThreads, 1)
 shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                    const uint8_t* __restrict__ g_index, int K, uint32_t* __restrict__ bitvecs, uint64_t stride_words,
-                   bool count_matches)
+                   unsigned long long* __restrict__ counts, bool count_matches, const IndexSmemPlan plan)
 {
     using Cfg = SharedCfg<W>;
+    using Rot = BlockRot<W, 1>;
     extern __shared__ __align__(128) uint8_t smem[];
-    // per-CTA interval histogram (match counts are derived from it, see predindex.cuh)
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);
-    for (int i = threadIdx.x; i < 2 * K + 1; i += kSThreads) s_hist[i] = 0;
-    const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + kCounterBytes, kSmem);
+    uint8_t* s_index = smem + Cfg::kRingBytes + plan.hist_bytes;
+    const IntervalHist hist = hist_init(smem + Cfg::kRingBytes, plan);  // kSmem: empty, the rows carry the counters
+    const PredIndexView ix = load_pred_index(g_index, s_index, plan);
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();  // contains the __syncthreads that publishes the index and the zeroed counters
 
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const int cols = (K + 31) >> 5;
+    const uint32_t lane_rot = Rot::lane_rot();
+    uint32_t direct[kDirectCountMaxK] = {};  // K <= 8: this thread's match counts
 
     uint32_t iter = 0;
     for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
@@ -68,86 +74,110 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
         const bool active = gb < n_blocks;
+        const bool last = tail_bits != 0 && gb == n_blocks - 1;  // the one ragged block of the column
+        // register j holds code (j + rot * kPieceCodes) mod 32; the ragged block is read unrotated
+        const uint32_t rot = last ? 0u : lane_rot;
         uint32_t x[W];
-#pragma unroll
-        for (int k = 0; k < W; k++) x[k] = active ? buf[threadIdx.x * W + k] : 0u;
+        load_block<W, 1>(buf, threadIdx.x, x, rot);
         uint32_t loaded = 0;
 #pragma unroll
         for (int k = 0; k < W; k++) loaded |= x[k];
         ring.release_warp(iter, tile, loaded);  // the stage is free once every warp has copied its words
-        if (active) {
-            const bool last = tail_bits != 0 && gb == n_blocks - 1;  // the one ragged block of the column
-            uint32_t id[32];
-            block_ids<W>(x, ix, id);
-            if (count_matches) {
-                if (!last) {
+        if (!active) continue;
+
+        const uint32_t unrot = rot * Rot::kPieceCodes;
+        const uint32_t keep = last ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
+        uint32_t id[32];
+        block_ids<W>(x, ix, id);
+        uint32_t* p = bitvecs + gb;  // this block's word of predicate 0; += stride_words per predicate
+        if (K <= kDirectCountMaxK) {  // one byte of predicates per code: the cheap 32 x 8 transpose
+            rows_of_ids<kSmem>(ix, id);
+            uint32_t m[32], r[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) atomicAdd(&s_hist[id[j]], 1u);
-                } else {
-                    for (uint32_t j = 0; j < tail_bits; j++) {
-                        uint32_t v = 0;
+            for (int j = 0; j < 32; j++) m[j] = row_mask_word<kSmem>(ix, id[j], 0);  // (no counter column: K <= 8)
+            transpose32x8(m, r);
 #pragma unroll
-                        for (int q = 0; q < 32; q++) v = (q == (int)j) ? id[q] : v;
-                        atomicAdd(&s_hist[v], 1u);
-                    }
+            for (int k = 0; k < 8; k++) {
+                if (k < K) {
+                    uint32_t v = r[k];
+                    if constexpr (Rot::kRot) v = __funnelshift_l(v, v, unrot);
+                    v &= keep;
+                    direct[k] += __popc(v);
+                    st_stream_u32(p, v);
                 }
+                p += stride_words;
             }
-            uint32_t* p = bitvecs + gb;  // this block's word of predicate 0; += stride_words per predicate
-            if (K <= 8) {  // one byte of predicates per code: the cheap 32 x 8 transpose
-                uint32_t m[32], r[8];
+            continue;
+        }
+        if (!kSmem && count_matches) {  // separate histogram, indexed by the interval id
+            if (!last) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) m[j] = mask_word<kSmem>(ix, id[j], 0);
-                transpose32x8(m, r);
-                const uint32_t keep = last ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
+                for (int j = 0; j < 32; j++) hist.add(id[j]);
+            } else {
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    if (k < K) st_stream_u32(p, r[k] & keep);
+                for (int j = 0; j < 32; j++)
+                    if ((uint32_t)j < tail_bits) hist.add(id[j]);
+            }
+        }
+        rows_of_ids<kSmem>(ix, id);
+        if (kSmem && count_matches) {  // the rows carry their interval's counter
+            if (!last) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) row_count(id[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if ((uint32_t)j < tail_bits) row_count(id[j]);
+            }
+        }
+        for (int c = 0; c < cols; c++) {
+            uint32_t m[32];
+            // derived from the kernel parameter so that it stays in a uniform register: LDS [R + UR]
+            const uint32_t col_bytes = kSmem ? (((uint32_t)c + plan.has_counter) << (plan.rep_log2 + 2)) : (uint32_t)c * 4u;
+#pragma unroll
+            for (int j = 0; j < 32; j++) m[j] = row_mask_word<kSmem>(ix, id[j], col_bytes);
+            transpose32(m);  // m[k'] bit j = predicate 32c+k' on code j
+            const int kk = K - 32 * c;  // predicates in this column
+            if (kk >= 32 && !last && !Rot::kRot) {
+#pragma unroll
+                for (int k = 0; k < 32; k++) {
+                    st_stream_u32(p, m[k]);
                     p += stride_words;
                 }
             } else {
-                for (int c = 0; c < cols; c++) {
-                    uint32_t m[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) m[j] = mask_word<kSmem>(ix, id[j], c);
-                    transpose32(m);  // m[k'] bit j = predicate 32c+k' on code j
-                    if (last) {
-                        const uint32_t keep = (1u << tail_bits) - 1u;
-#pragma unroll
-                        for (int k = 0; k < 32; k++) m[k] &= keep;
-                    }
-                    const int kk = K - 32 * c;  // predicates in this column
-                    if (kk >= 32) {
-#pragma unroll
-                        for (int k = 0; k < 32; k++) {
-                            st_stream_u32(p, m[k]);
-                            p += stride_words;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 32; k++) {
-                            if (k < kk) st_stream_u32(p, m[k]);
-                            p += stride_words;
-                        }
-                    }
+                for (int k = 0; k < 32; k++) {
+                    uint32_t v = m[k];
+                    if constexpr (Rot::kRot) v = __funnelshift_l(v, v, unrot);
+                    if (k < kk) st_stream_u32(p, v & keep);
+                    p += stride_words;
                 }
             }
         }
     }
     __syncthreads();
     if (count_matches) {
-        unsigned long long* g_hist =
-            reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(g_index) + PredIndexLayout::kHist);
-        for (uint32_t i = threadIdx.x; i <= ix.num_bp; i += kSThreads)
-            if (s_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)s_hist[i]);
+        if (K <= kDirectCountMaxK) {
+#pragma unroll
+            for (int k = 0; k < kDirectCountMaxK; k++) {
+                const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, direct[k]);
+                if ((threadIdx.x & 31) == 0 && k < K && s != 0) atomicAdd(&counts[k], (unsigned long long)s);
+            }
+        } else if (kSmem) {
+            merged_hist_flush(ix, plan, s_index, g_index);
+        } else {
+            hist_flush(smem + Cfg::kRingBytes, plan, ix.num_bp, g_index);
+        }
     }
 }
 
 template <int W, bool kSmem>
 static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, const void* index, int K,
-                             uint32_t* bitvecs, uint64_t stride_words, bool count_matches, size_t smem,
-                             cudaStream_t stream)
+                             uint32_t* bitvecs, uint64_t stride_words, unsigned long long* counts, bool count_matches,
+                             const IndexSmemPlan& plan, cudaStream_t stream)
 {
     using Cfg = SharedCfg<W>;
+    const size_t smem = Cfg::kRingBytes + plan.total_bytes;
     static size_t configured[64] = {};
     if (configured[dev.ordinal & 63] < smem) {
         cudaError_t e = cudaFuncSetAttribute(shared_scan_kernel<W, kSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -158,27 +188,28 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
     const uint64_t n_blocks = (n + 31) / 32;
     const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
-    const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
+    const uint64_t max_ctas = (uint64_t)dev.sm_count;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(
-        packed, readable, n, static_cast<const uint8_t*>(index), K, bitvecs, stride_words, count_matches);
+    shared_scan_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(packed, readable, n,
+                                                                   static_cast<const uint8_t*>(index), K, bitvecs,
+                                                                   stride_words, counts, count_matches, plan);
     return cudaGetLastError();
 }
 
 template <int W>
 static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K,
-                            uint32_t* bitvecs, uint64_t stride_words, bool count_matches, cudaStream_t stream)
+                            uint32_t* bitvecs, uint64_t stride_words, unsigned long long* counts, bool count_matches,
+                            cudaStream_t stream)
 {
-    bool masks_in_smem = false;
-    const size_t other = SharedCfg<W>::kRingBytes + kCounterBytes;
-    const size_t smem = other + pred_index_smem_bytes(K, W, other, &masks_in_smem) + 64;
-    if (masks_in_smem)
-        return launch_ws<W, true>(dev, packed, n, index, K, bitvecs, stride_words, count_matches, smem, stream);
-    return launch_ws<W, false>(dev, packed, n, index, K, bitvecs, stride_words, count_matches, smem, stream);
+    const IndexSmemPlan plan =
+        plan_index_smem(K, W, SharedCfg<W>::kRingBytes, /*use_hist=*/K > kDirectCountMaxK, /*merged_ok=*/true);
+    if (plan.masks_in_smem)
+        return launch_ws<W, true>(dev, packed, n, index, K, bitvecs, stride_words, counts, count_matches, plan, stream);
+    return launch_ws<W, false>(dev, packed, n, index, K, bitvecs, stride_words, counts, count_matches, plan, stream);
 }
 
-using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, uint32_t*, uint64_t, bool,
-                                 cudaStream_t);
+using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, uint32_t*, uint64_t,
+                                 unsigned long long*, bool, cudaStream_t);
 
 template <int... Ws>
 static constexpr auto make_table(std::integer_sequence<int, Ws...>)
@@ -187,10 +218,11 @@ static constexpr auto make_table(std::integer_sequence<int, Ws...>)
 }
 
 cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n, int w, const void* index, int K,
-                               uint32_t* bitvecs, uint64_t stride_words, bool count_matches, cudaStream_t stream)
+                               uint32_t* bitvecs, uint64_t stride_words, unsigned long long* counts, bool count_matches,
+                               cudaStream_t stream)
 {
     static constexpr auto table = make_table(std::make_integer_sequence<int, 32>{});
-    return table[w - 1](dev, packed, n, index, K, bitvecs, stride_words, count_matches, stream);
+    return table[w - 1](dev, packed, n, index, K, bitvecs, stride_words, counts, count_matches, stream);
 }
 
 }  // namespace sss

@@ -108,19 +108,29 @@ struct SwarConsts {
     uint32_t lo_top;  // top bit of lo (selects the kernel instantiation; kept for reference)
 };
 
+#if defined(__CUDA_ARCH__)
+#define SSS_UNROLL _Pragma("unroll")
+#else
+#define SSS_UNROLL
+#endif
+
 template <int W>
-inline SwarConsts<W> make_swar_consts(uint32_t lo, uint32_t hi)
+SSS_HD inline SwarConsts<W> make_swar_consts(uint32_t lo, uint32_t hi)
 {
     SwarConsts<W> c{};
     const uint32_t msb = 1u << (W - 1);
     const uint32_t d = hi - lo;
-    auto put = [&](uint32_t* dst, uint32_t v) {
+    // every index below is a compile-time constant once the loops are unrolled, so that in device
+    // code (scan_range_dev_kernel builds its constants itself) the arrays stay in registers
+    auto put = [&](uint32_t (&dst)[W], uint32_t v) {
+        SSS_UNROLL
         for (int i = 0; i < W; i++) dst[i] = 0;
+        SSS_UNROLL
         for (int j = 0; j < 32; j++) {
             const int p = j * W;
             const unsigned long long vv = (unsigned long long)v << (p & 31);
             dst[p >> 5] |= (uint32_t)vv;
-            if ((p >> 5) + 1 < W) dst[(p >> 5) + 1] |= (uint32_t)(vv >> 32);
+            if ((p >> 5) + 1 < W) dst[(p >> 5) + 1 < W ? (p >> 5) + 1 : 0] |= (uint32_t)(vv >> 32);
         }
     };
     put(c.lol, lo & ~msb);
