@@ -47,8 +47,9 @@ struct ScanPlan {
 #ifndef SSS_SCAN_MAX_CTAS
 #define SSS_SCAN_MAX_CTAS 2
 #endif
-    static constexpr int kR =
-        (SSS_SCAN_TILE_WORDS / kGroupWords) > 1 ? (SSS_SCAN_TILE_WORDS / kGroupWords) : 1;  // groups per thread per tile
+    // (W = 1 runs ring-less, one CTA per tile -- scan_direct_kernel -- and does best with 32 words per thread)
+    static constexpr int kTileWords = (W == 1) ? 32 : SSS_SCAN_TILE_WORDS;
+    static constexpr int kR = (kTileWords / kGroupWords) > 1 ? (kTileWords / kGroupWords) : 1;  // groups per thread per tile
     static constexpr int kBlocksPerTile = kThreads * kR * kG;                                // = result words per tile
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
     static constexpr int kStages = ring_stages(kTileBytes);
@@ -224,6 +225,35 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
     if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
 }
 
+// One-bit codes without the ring: one CTA per tile, the tile read straight from global memory with
+// 128-bit loads.  A 2^30-code scan at W = 1 is a ~50 us kernel whose output is as large as its input;
+// there the ring's prologue and the persistent CTAs' drain are a visible share of the launch, and a
+// plain grid of short-lived CTAs keeps more of the machine busy at both ends.
+// Measured (profiles/r01_ab_scan_narrow.txt): +5 % at W = 1, nothing at W = 2, 3.
+#ifndef SSS_SCAN_DIRECT_MAXW
+#define SSS_SCAN_DIRECT_MAXW 1
+#endif
+template <int W, int kMode>
+__global__ void __launch_bounds__(kThreads)
+scan_direct_kernel(const void* __restrict__ packed, uint64_t n, const __grid_constant__ ScanArgs<W> args,
+                   uint32_t* __restrict__ bitvec, unsigned long long* __restrict__ count,
+                   unsigned long long* __restrict__ count_slot, bool accumulate)
+{
+    using P = ScanPlan<W>;
+    const uint64_t n_blocks = (n + 31) >> 5;
+    const uint64_t full_blocks = n >> 5;
+    const uint32_t tail_bits = (uint32_t)(n & 31);
+    const uint64_t tile_block0 = blockIdx.x * (uint64_t)P::kBlocksPerTile;
+    const uint32_t* buf = static_cast<const uint32_t*>(packed) + tile_block0 * W;
+    uint32_t* tile_out = bitvec + tile_block0;
+    uint32_t hits;
+    if (tile_block0 + P::kBlocksPerTile <= full_blocks)
+        hits = scan_tile<W, kMode, false>(buf, args, 0u, tile_out, 0, 0);
+    else
+        hits = scan_tile<W, kMode, true>(buf, args, 0u, tile_out, n_blocks - tile_block0, tail_bits);
+    if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
+}
+
 // The same scan with its bounds in DEVICE memory: a shared scan with a single predicate is this
 // kernel (one bitvector, one count -- for K = 1 the linear layout is the bitvector too), and the
 // shared-scan entry points take their bounds as device arrays.  The per-launch constants that
@@ -286,6 +316,13 @@ static cudaError_t launch_mode(const Device& dev, const void* packed, uint64_t n
     const uint64_t n_blocks = (n + 31) / 32;
     const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
     const uint64_t tiles = (readable + P::kTileBytes - 1) / P::kTileBytes;
+    if constexpr (W <= SSS_SCAN_DIRECT_MAXW) {
+        if (tiles < (1ull << 31)) {
+            scan_direct_kernel<W, kMode><<<(unsigned)tiles, kThreads, 0, stream>>>(packed, n, args, bitvec, ct.result,
+                                                                                 ct.slot, ct.accumulate);
+            return cudaGetLastError();
+        }
+    }
     const uint64_t max_ctas = (uint64_t)dev.sm_count * P::kCtasPerSm;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     scan_range_kernel<W, kMode><<<grid, kThreads, smem, stream>>>(packed, readable, n, args, bitvec, ct.result, ct.slot,

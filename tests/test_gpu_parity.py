@@ -311,6 +311,49 @@ def test_many_predicates(sss, w, K):
     assert (host(cnt).astype(np.uint64) == ecnt).all()
 
 
+@pytest.mark.parametrize("w", [2, 8, 13, 20, 24, 28])
+@pytest.mark.parametrize("K", [2, 16, 100, 128, 512])
+def test_shared_scan_store_paths_and_row_tables(sss, w, K):
+    """Widths with rotated block loads (8, 24), 64-bit (2 mod 4) and 128-bit (4 mod 8) block loads, and
+    predicate counts that exercise the single-store rows (K = 2), 16-byte row pieces (K = 16), ragged
+    columns (K = 100) and partially replicated row tables (K = 128, 512), over several tiles."""
+    n = 40_003
+    rng = np.random.default_rng(w * 97 + K)
+    m = (1 << w) - 1
+    codes, packed = column(n, w, seed=700 + w)
+    lo = rng.integers(0, m + 1, size=K, dtype=np.uint64)
+    hi = np.minimum(lo + rng.integers(0, max(2, (m + 1) // 8), size=K, dtype=np.uint64), m)
+    hi[::3] = lo[::3]
+    exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
+    bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi)
+    nb = (n + 7) // 8
+    assert (host(bv)[:, :nb] == exp).all()
+    assert (host(cnt).astype(np.uint64) == ecnt).all()
+    lexp, lcnt = B.shared_scan_linear(packed, n, w, lo, hi, granule=1)
+    lin, cnt2 = sss.shared_scan_linear(dev(packed), n, w, lo, hi)
+    assert (host(lin)[:nb] == lexp).all()
+    assert not host(lin)[nb:].any()
+    assert (host(cnt2).astype(np.uint64) == lcnt).all()
+
+
+def test_shared_scan_wide_kernel_unaligned_stride(sss):
+    """K > 512 with a bitvector stride that is not a multiple of 32 bytes: the warp-per-block kernel
+    must fall back from its 256-bit stores to word stores."""
+    w, K, n = 11, 640, 33_000
+    rng = np.random.default_rng(5)
+    m = (1 << w) - 1
+    codes, packed = column(n, w, seed=811)
+    lo = rng.integers(0, m + 1, size=K, dtype=np.uint64)
+    hi = np.minimum(lo + rng.integers(0, 200, size=K, dtype=np.uint64), m)
+    exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
+    stride = 4 * ((n + 31) // 32) + 4                      # whole words, but 4 mod 32 bytes
+    out = torch.zeros((K, stride), dtype=torch.uint8, device="cuda")
+    bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi, out=out)
+    nb = (n + 7) // 8
+    assert (host(bv)[:, :nb] == exp).all()
+    assert (host(cnt).astype(np.uint64) == ecnt).all()
+
+
 @pytest.mark.parametrize("w,K", [(17, 64), (9, 64), (23, 8)])
 def test_shared_scan_full_size_properties(sss, w, K):
     """2^28 codes: every shared-scan bitvector equals the single scan of its predicate (itself
