@@ -153,7 +153,7 @@ __device__ __forceinline__ uint32_t code_id_runtime(const uint32_t* blk, uint32_
     const uint32_t bit = j * W, wi = bit >> 5;
     const uint32_t v = __funnelshift_r(blk[wi], blk[wi + 1 < (uint32_t)W ? wi + 1 : wi], bit & 31) & code_mask(W);
     if constexpr (W <= kDirectMaxW) {
-        return static_cast<const uint16_t*>(ix.locator)[v];
+        return static_cast<const uint32_t*>(ix.locator)[v];
     } else {
         const uint32_t t = v << (32 - W);
         const uint32_t e = static_cast<const uint32_t*>(ix.locator)[t >> (32 - kBucketBits)];

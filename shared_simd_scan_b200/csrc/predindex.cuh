@@ -12,7 +12,7 @@
 //   breakpoints  bp[0..M)   sorted, distinct: every lo_k (> 0) and hi_k + 1 (<= 2^W - 1)
 //   interval id  id(v) = #{ i : bp[i] <= v }                      in [0, M]
 //   mask rows    mask[id][k] = 1  iff  lo_k <= start(id) <= hi_k   ceil(K/32) words per row
-//   locator      W <= 13 : lut[v] = id(v) * row_bytes             (direct, 2 bytes per code value)
+//   locator      W <= 13 : lut[v] = id(v)                        (direct; 16-bit entries in global memory)
 //                W  > 13 : 8192 buckets on the top 13 bits of the code, ONE 32-bit word each:
 //                          [threshold : 19][several breakpoints inside : 1][id at bucket start : 12];
 //                          a bucket with at most one inner breakpoint resolves with one compare of the
@@ -76,7 +76,9 @@ cudaError_t launch_counts_from_histogram(void* d_index, int K, unsigned long lon
 
 struct PredIndexView {
     const uint32_t* thr;      // shared
-    const void* locator;      // shared
+    const void* locator;      // shared (replica 0; plain indexing is valid only without replicas)
+    uint32_t loc_saddr;       // shared-window address of this lane's replica of locator entry 0
+    uint32_t loc_stride;      // bytes between consecutive locator entries (entry size x replicas)
     const uint32_t* masks;    // global table (kSmem = false)
     uint32_t rows_saddr;      // shared-window address of this lane's replica of row 0 (kSmem = true)
     uint32_t row_bytes;       // bytes between the rows of consecutive intervals
@@ -96,6 +98,7 @@ struct PredIndexView {
 // interleaved word by word, lane l uses copy l mod R; at R = 32 every lane stays in its own bank
 // and every access is a single wavefront.
 //
+//   locator (merged plans): entry e of replica r at (e * R_l + r) entries; sized after the rows.
 //   merged rows (thread-per-block kernels, table fits):
 //       row[id] = [match counter][mask column 0][mask column 1]..., each R words; one multiply-add
 //       turns an interval id into the address of its row = of its counter, the mask columns are at
@@ -108,6 +111,7 @@ struct IndexSmemPlan {
     uint32_t row_groups;      // merged: row stride in R-word groups
     uint32_t has_counter;     // merged: group 0 of every row is the interval's match counter
     uint32_t masks_in_smem;
+    uint32_t loc_rep_log2;    // replicas of the locator (merged plans only; from what the rows leave over)
     uint32_t hist_rep_log2;   // separate: replicas of the histogram
     uint32_t hist_bytes;      // separate: bytes of the histogram in front of the index (0: none)
     uint32_t total_bytes;     // everything after the ring
@@ -119,7 +123,8 @@ inline IndexSmemPlan plan_index_smem(int K, int w, size_t ring_bytes, bool use_h
     IndexSmemPlan p{};
     const size_t cols = ((size_t)K + 31) / 32;
     const size_t max_rows = (w >= 31) ? (size_t)(2 * K + 1) : std::min<size_t>((size_t)2 * K + 1, (size_t)1 << w);
-    const size_t locator = (w <= kDirectMaxW) ? ((size_t)2 << w) : (size_t)kBuckets * 4;
+    // (in shared memory the direct table is widened to 32-bit entries: one entry per bank and lane)
+    const size_t locator = (w <= kDirectMaxW) ? ((size_t)4 << w) : (size_t)kBuckets * 4;
     const size_t thr = (w <= kDirectMaxW) ? 0 : (std::min<size_t>(2 * (size_t)K, kMaxBp) + 1) * 4;
     const size_t index = up16(locator) + up16(thr) + 64;
     const size_t budget = (size_t)kSharedSmemBudget;
@@ -134,7 +139,10 @@ inline IndexSmemPlan plan_index_smem(int K, int w, size_t ring_bytes, bool use_h
                 p.rep_log2 = (uint32_t)r;
                 p.row_groups = (uint32_t)groups;
                 p.has_counter = use_hist ? 1u : 0u;
-                p.total_bytes = (uint32_t)(index + bytes);
+                while (p.loc_rep_log2 < 5 &&
+                       ring_bytes + up16(locator << (p.loc_rep_log2 + 1)) + up16(thr) + 64 + bytes <= budget)
+                    p.loc_rep_log2++;
+                p.total_bytes = (uint32_t)(up16(locator << p.loc_rep_log2) + up16(thr) + 64 + bytes);
                 return p;
             }
         }
@@ -166,7 +174,8 @@ __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restri
     v.num_bp = h->num_bp;
     v.direct = h->direct != 0;
     const uint32_t g_row_words = h->row_words;
-    const uint32_t locator_bytes = v.direct ? (2u << h->w) : (uint32_t)kBuckets * 4;
+    const uint32_t lr = plan.loc_rep_log2, LR = 1u << lr;
+    const uint32_t locator_bytes = (v.direct ? (4u << h->w) : (uint32_t)kBuckets * 4) << lr;
     const uint32_t thr_bytes = v.direct ? 0u : (v.num_bp + 1) * 4;  // + the 0xFFFFFFFF sentinel
     uint8_t* s_loc = smem;
     uint8_t* s_thr = s_loc + ((locator_bytes + 15) & ~15u);
@@ -176,9 +185,21 @@ __device__ __forceinline__ PredIndexView load_pred_index(const uint8_t* __restri
         for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x)
             reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
     };
-    copy(s_loc, g_index + PredIndexLayout::kLocator, locator_bytes);
+    if (v.direct) {  // 16-bit entries in global memory, widened here; LR replicas each
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(g_index + PredIndexLayout::kLocator);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_loc);
+        for (uint32_t i = threadIdx.x; i < ((1u << h->w) << lr); i += blockDim.x) dst[i] = src[i >> lr];
+    } else if (lr == 0) {
+        copy(s_loc, g_index + PredIndexLayout::kLocator, locator_bytes);
+    } else {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kLocator);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_loc);
+        for (uint32_t i = threadIdx.x; i < ((uint32_t)kBuckets << lr); i += blockDim.x) dst[i] = __ldg(src + (i >> lr));
+    }
     copy(s_thr, g_index + PredIndexLayout::kThr, thr_bytes);
     v.locator = s_loc;
+    v.loc_saddr = smem_u32(s_loc) + (threadIdx.x & (LR - 1)) * 4u;
+    v.loc_stride = 4u << lr;
     v.thr = reinterpret_cast<const uint32_t*>(s_thr);
     const uint32_t* g_masks = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kMasks);
     v.masks = g_masks;
@@ -218,7 +239,7 @@ __device__ __forceinline__ void merged_hist_flush(const PredIndexView& ix, const
     const uint32_t R = 1u << plan.rep_log2;
     // recompute the table base the way load_pred_index laid it out
     const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(g_index + PredIndexLayout::kHeader);
-    const uint32_t locator_bytes = ix.direct ? (2u << h->w) : (uint32_t)kBuckets * 4;
+    const uint32_t locator_bytes = (ix.direct ? (4u << h->w) : (uint32_t)kBuckets * 4) << plan.loc_rep_log2;
     const uint32_t thr_bytes = ix.direct ? 0u : (ix.num_bp + 1) * 4;
     const uint32_t* rows =
         reinterpret_cast<const uint32_t*>(s_index + ((locator_bytes + 15) & ~15u) + ((thr_bytes + 15) & ~15u));
@@ -355,6 +376,14 @@ SSS_HD inline uint32_t make_bucket_word(uint32_t id_at_start, bool several, uint
     return (thr19 << kBucketBits) | (several ? kSeveralBit : 0u) | id_at_start;
 }
 
+// entry `idx` of this lane's replica of the locator: one multiply-add for the address
+__device__ __forceinline__ uint32_t locator_entry(const PredIndexView& ix, uint32_t idx)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(idx * ix.loc_stride + ix.loc_saddr));
+    return v;
+}
+
 template <int W, int J>
 struct BlockIds {
     static __device__ __forceinline__ void fast(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&id)[32],
@@ -362,9 +391,9 @@ struct BlockIds {
     {
         const uint32_t t = left_aligned_code<W, J>(x);
         if constexpr (W <= kDirectMaxW) {
-            id[J] = static_cast<const uint16_t*>(ix.locator)[t >> (32 - W)];
+            id[J] = locator_entry(ix, t >> (32 - W));
         } else {
-            const uint32_t e = static_cast<const uint32_t*>(ix.locator)[t >> (32 - kBucketBits)];
+            const uint32_t e = locator_entry(ix, t >> (32 - kBucketBits));
             id[J] = (e & kBucketIdMask) + ((t << kBucketBits) > e ? 1u : 0u);
             flags |= e;
         }
@@ -376,7 +405,7 @@ struct BlockIds {
     {
         if constexpr (W > kDirectMaxW) {
             const uint32_t t = left_aligned_code<W, J>(x);
-            const uint32_t e = static_cast<const uint32_t*>(ix.locator)[t >> (32 - kBucketBits)];
+            const uint32_t e = locator_entry(ix, t >> (32 - kBucketBits));
             if (e & kSeveralBit) {
                 uint32_t i = e & kBucketIdMask;
                 while (t > ix.thr[i]) i++;

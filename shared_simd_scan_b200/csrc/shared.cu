@@ -66,6 +66,8 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const int cols = (K + 31) >> 5;
     const uint32_t lane_rot = Rot::lane_rot();
+    const bool narrow = stride_words < (1ull << 30);  // bitvector stride below 4 GiB
+    const uint32_t stride_bytes32 = (uint32_t)(stride_words * 4);
     uint32_t direct[kDirectCountMaxK] = {};  // K <= 8: this thread's match counts
 
     uint32_t iter = 0;
@@ -138,7 +140,15 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
             for (int j = 0; j < 32; j++) m[j] = row_mask_word<kSmem>(ix, id[j], col_bytes);
             transpose32(m);  // m[k'] bit j = predicate 32c+k' on code j
             const int kk = K - 32 * c;  // predicates in this column
-            if (kk >= 32 && !last && !Rot::kRot) {
+            if (kk >= 32 && !last && !Rot::kRot && narrow) {
+                // address of predicate k's word = p + k * stride: one IMAD.WIDE each (FMA pipe) instead of
+                // a 64-bit add chain (two ALU instructions per store)
+#pragma unroll
+                for (int k = 0; k < 32; k++)
+                    st_stream_u32(reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p) +
+                                                              (uint64_t)stride_bytes32 * (uint32_t)k), m[k]);
+                p += 32 * stride_words;
+            } else if (kk >= 32 && !last && !Rot::kRot) {
 #pragma unroll
                 for (int k = 0; k < 32; k++) {
                     st_stream_u32(p, m[k]);
@@ -205,7 +215,7 @@ __device__ __forceinline__ uint32_t wide_code_id(const uint32_t* blk, uint32_t j
     const uint32_t bit = j * W, wi = bit >> 5;
     const uint32_t v = __funnelshift_r(blk[wi], blk[wi + 1 < (uint32_t)W ? wi + 1 : wi], bit & 31) & code_mask(W);
     if constexpr (W <= kDirectMaxW) {
-        return static_cast<const uint16_t*>(ix.locator)[v];
+        return static_cast<const uint32_t*>(ix.locator)[v];
     } else {
         const uint32_t t = v << (32 - W);
         const uint32_t e = static_cast<const uint32_t*>(ix.locator)[t >> (32 - kBucketBits)];

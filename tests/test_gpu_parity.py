@@ -339,7 +339,7 @@ def test_shared_scan_store_paths_and_row_tables(sss, w, K):
 def test_shared_scan_wide_kernel_unaligned_stride(sss):
     """K > 512 with a bitvector stride that is not a multiple of 32 bytes: the warp-per-block kernel
     must fall back from its 256-bit stores to word stores."""
-    w, K, n = 11, 640, 33_000
+    w, K, n = 24, 640, 33_000
     rng = np.random.default_rng(5)
     m = (1 << w) - 1
     codes, packed = column(n, w, seed=811)
