@@ -345,14 +345,10 @@ def run_ours(args):
     counts = torch.zeros(len(WIDTHS), dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
 
-    def step(events=None):
+    def step():
         for i, w in enumerate(WIDTHS):
-            if events is not None:
-                events[i].record()
             lo, hi = predicate(w)
             api.scan(columns[w], n, w, lo, hi, out=bitvec, count=counts[i:i + 1])
-        if events is not None:
-            events[len(WIDTHS)].record()
         if world > 1:
             dist.all_reduce(counts)  # the only collective on the path: 32 x int64
 
@@ -368,13 +364,12 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(WIDTHS) + 1)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.perf_counter()
     t_begin.record()
     for k in range(args.steps):
-        step(ev[k])
+        step()
     t_end.record()
     barrier()
     wall1 = time.perf_counter()
@@ -387,19 +382,30 @@ def run_ours(args):
     ms_per_step = dev_ms / args.steps
     value = world * len(WIDTHS) * n / (ms_per_step * 1e-3)
 
-    # per-width kernel time (events bracket each launch on the launching stream)
-    per_width = []
-    total_kernel_ms, total_bytes = 0.0, 0.0
-    for i, w in enumerate(WIDTHS):
-        ms = statistics.mean(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps))
-        b = n * (w / 8 + 1 / 8)
-        total_kernel_ms += ms
-        total_bytes += b
-        per_width.append({"w": w, "ms": round(ms, 4), "gcodes_per_s": round(n / ms / 1e6, 1),
-                          "gb_per_s": round(b / ms / 1e6, 1), "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4),
-                          "frac_of_8TBps": round(b / ms / 1e6 / 8000.0, 4)})
-    achieved = total_bytes / (total_kernel_ms * 1e-3) / 1e9
+    # roofline of the step's kernel (32 launches of scan_range_kernel<W>): algorithmic bytes of a step over the
+    # device time of a step, both from the timed region above (so launch gaps count against the kernel)
+    total_bytes = sum(n * (w / 8 + 1 / 8) for w in WIDTHS)
+    achieved = total_bytes / (ms_per_step * 1e-3) / 1e9
     final_counts = counts.cpu().tolist()
+
+    # per-width launch duration, after the timed region: `reps` back-to-back launches of one width between
+    # two events on the launching stream (an event pair around a single 50 us launch would add ~20 %)
+    per_width = []
+    reps = 10
+    for i, w in enumerate(WIDTHS):
+        lo, hi = predicate(w)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        api.scan(columns[w], n, w, lo, hi, out=bitvec, count=counts[i:i + 1])
+        a.record()
+        for _ in range(reps):
+            api.scan(columns[w], n, w, lo, hi, out=bitvec, count=counts[i:i + 1])
+        b.record()
+        b.synchronize()
+        ms = a.elapsed_time(b) / reps
+        nb = n * (w / 8 + 1 / 8)
+        per_width.append({"w": w, "ms": round(ms, 4), "gcodes_per_s": round(n / ms / 1e6, 1),
+                          "gb_per_s": round(nb / ms / 1e6, 1), "frac_of_measured_peak": round(nb / ms / 1e6 / peak, 4),
+                          "frac_of_8TBps": round(nb / ms / 1e6 / 8000.0, 4)})
 
     # ---- e2e: the host-buffer C-ABI call (what include/simd_scan.hpp wraps), pinned host memory ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -448,8 +454,9 @@ def run_ours(args):
                      "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 32 launches of "
                                        "one step at 2^30 codes (profiles/r01_scan_traffic.json)",
                      "peak_source": peak_src,
-                     "kernel": "sss::scan_range_kernel<W>, aggregated over the 32 launches of a step "
-                               "(bytes = n*(w/8+1/8) per launch; per-launch numbers in per_width)",
+                     "kernel": "sss::scan_range_kernel<W> (W = 1: scan_direct_kernel), the 32 launches of a step: "
+                               "bytes = sum of n*(w/8+1/8), time = the step's device time in the timed region "
+                               "(per-width launch durations in per_width: 10 back-to-back launches per event pair)",
                      "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},
         "per_width": per_width,
     }
@@ -494,6 +501,8 @@ def extras(args, api, columns, n, peak):
         return a.elapsed_time(b) / reps
 
     out = {"shared": [], "unpack": [], "pack": [], "positions": []}
+    if not args.no_sweep:
+        out["shared_sweep"] = shared_sweep(args, api, columns, n, peak)
     g = torch.Generator().manual_seed(42)
     for kind, w, K, logn in (("shared", 17, 8, 30), ("shared", 17, 64, 30), ("shared", 23, 64, 30),
                              ("linear", 9, 64, 30), ("linear", 9, 1024, 27)):
@@ -550,6 +559,58 @@ def extras(args, api, columns, n, peak):
     return out
 
 
+def shared_sweep(args, api, columns, n, peak):
+    """The metric's table: shared scan (K bitvectors + K counts) and linear-layout shared scan at EVERY
+    bit width 1..32 and K in {1, 8, 64, 1024}, device-resident (same method as tools/sweep_wk.py: K
+    uniform-random ranges, 2 warm-ups, best of 5 by CUDA events).  n is halved until the output fits a
+    16 GiB arena (K = 1024: 2^27 codes).  Rows are [op, w, K, log2 n, ms, G codes/s, GB/s, fraction of
+    the measured HBM peak]; bytes = n * (w/8 + K/8)."""
+    import math
+
+    import torch
+
+    max_out = 16 << 30
+    arena = torch.empty(max_out + (1 << 20), dtype=torch.uint8, device="cuda")
+    rows = []
+    for w in WIDTHS:
+        m = (1 << w) - 1
+        for K in (1, 8, 64, 1024):
+            n2 = n
+            while K * (n2 // 8) > max_out:
+                n2 //= 2
+            g = torch.Generator().manual_seed(42 + K)
+            lo = torch.randint(0, m + 1, (K,), generator=g)
+            hi = torch.clamp(lo + torch.randint(0, max(2, 2 * (m + 1) // K), (K,), generator=g), max=m)
+            lo_d, hi_d = lo.to(torch.int32).cuda(), hi.to(torch.int32).cuda()
+            cnt = torch.empty(K, dtype=torch.int64, device="cuda")
+            for op in ("shared", "linear"):
+                if op == "shared":
+                    stride = (api.bitvec_bytes(n2) + 31) // 32 * 32
+                    buf = arena[: K * stride].view(K, stride)
+                    fn = lambda: api.shared_scan(columns[w], n2, w, lo_d, hi_d, out=buf, counts=cnt)  # noqa: E731
+                else:
+                    nrows = 4 * ((n2 + 31) // 32)
+                    buf = arena[: nrows * K].view(nrows, K)
+                    fn = lambda: api.shared_scan_linear(columns[w], n2, w, lo_d, hi_d, out=buf, counts=cnt)  # noqa: E731
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                best = float("inf")
+                for _ in range(5):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    fn()
+                    b.record()
+                    b.synchronize()
+                    best = min(best, a.elapsed_time(b))
+                nbytes = n2 * (w / 8 + K / 8)
+                rows.append([op, w, K, int(math.log2(n2)), round(best, 4), round(n2 / best / 1e6, 1),
+                             round(nbytes / best / 1e6, 1), round(nbytes / best / 1e6 / peak, 4)])
+    del arena
+    return {"columns": ["op", "w", "K", "log2_n", "ms", "gcodes_per_s", "gb_per_s", "frac_of_measured_peak"],
+            "rows": rows}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -564,6 +625,7 @@ def main():
                     help="sweep = the contract line; cfg5 = optional sharded shared scan (K=64, 23 bit)")
     ap.add_argument("--cfg5-logn", type=int, default=31, help="cfg5: log2 codes per GPU")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the (w x K) shared-scan table of the extras")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner,

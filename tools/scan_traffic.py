@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One fused-scan launch per bit width at the bench size, for an ncu DRAM-traffic capture:
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-      -k regex:scan_range_kernel --csv --log-file gpurun_out/scan_traffic.csv python tools/scan_traffic.py
+      -k 'regex:scan_(range|direct)_kernel' --csv --log-file gpurun_out/scan_traffic.csv python tools/scan_traffic.py
 The result is summarised into profiles/ by tools/summarise_traffic.py and read by bench.py."""
 import os
 import sys

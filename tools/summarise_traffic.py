@@ -10,7 +10,7 @@ rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit()]
 per = {}
 for r in rows:
     name, metric, unit, val = r[4], r[-3], r[-2], float(r[-1].replace(",", ""))
-    m = re.search(r"scan_range_kernel<\(?(?:int\))?(\d+)", name)
+    m = re.search(r"scan_(?:range|direct)_kernel<\(?(?:int\))?(\d+)", name)
     if not m:
         continue
     w = int(m.group(1))
