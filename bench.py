@@ -500,7 +500,7 @@ def extras(args, api, columns, n, peak):
         b.synchronize()
         return a.elapsed_time(b) / reps
 
-    out = {"shared": [], "unpack": [], "pack": [], "positions": []}
+    out = {"shared": [], "unpack": [], "pack": [], "positions": [], "calibration": calibration(api, timed, peak)}
     if not args.no_sweep:
         out["shared_sweep"] = shared_sweep(args, api, columns, n, peak)
     g = torch.Generator().manual_seed(42)
@@ -557,6 +557,28 @@ def extras(args, api, columns, n, peak):
         out["unpack"].append({"w": w, "n": n2, "ms": round(ms, 4), "gcodes_per_s": round(n2 / ms / 1e6, 1),
                               "gb_per_s": round(b / ms / 1e6, 1), "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4)})
     return out
+
+
+def calibration(api, timed, peak):
+    """HBM bandwidth for the access mixes of this path (the reference's
+    bench_memory / bench_memcpy, src/benchmark_misc.cpp:9-52): streaming read, write, copy, and
+    read:write = W:1 (the traffic shape of the fused scan at W bits) over 4 GiB.  GB/s counts the bytes
+    actually moved; `vs_copy_peak` is against MEASURED_PEAKS.json, the roofline denominator."""
+    import torch
+
+    nbytes = 4 << 30
+    a = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    b = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    a.random_(0, 256)
+    rows = []
+    for mode, ratio in (("read", 1), ("write", 1), ("copy", 1), ("mix", 1), ("mix", 2), ("mix", 4), ("mix", 8),
+                        ("mix", 16), ("mix", 32)):
+        ms = timed(lambda: api.calibrate(mode, a, b, nbytes, ratio), reps=5, warm=2)
+        moved = {"read": nbytes, "write": nbytes, "copy": 2 * nbytes}.get(mode, nbytes + nbytes // ratio)
+        rows.append({"mode": mode if mode != "mix" else f"read:write = {ratio}:1", "gb_per_s": round(moved / ms / 1e6, 1),
+                     "vs_copy_peak": round(moved / ms / 1e6 / peak, 4)})
+    del a, b
+    return rows
 
 
 def shared_sweep(args, api, columns, n, peak):

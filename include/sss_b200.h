@@ -116,6 +116,17 @@ int sss_bitvec_combine(sss_ctx* ctx, int op, const void* d_a, const void* d_b, u
 int sss_unpack_at(sss_ctx* ctx, const void* d_packed, int w, const uint64_t* d_positions, uint64_t num,
                   int32_t* d_out, void* stream);
 
+/* Memory-bandwidth calibration (replaces bench_memory<T> / bench_memcpy, src/benchmark_misc.cpp:9-52):
+ * one streaming pass with the access mix of this path, to be timed by the caller.
+ *   SSS_CALIB_READ  reads `bytes` from d_a          SSS_CALIB_WRITE writes `bytes` to d_b
+ *   SSS_CALIB_COPY  d_a -> d_b, `bytes` each way    SSS_CALIB_MIX   reads `bytes`, writes bytes/ratio
+ * (MIX with ratio = W is the traffic shape of the fused scan at W bits).  Buffers 16-byte aligned. */
+#define SSS_CALIB_READ 0
+#define SSS_CALIB_WRITE 1
+#define SSS_CALIB_COPY 2
+#define SSS_CALIB_MIX 3
+int sss_calibrate(sss_ctx* ctx, int mode, const void* d_a, void* d_b, uint64_t bytes, uint32_t ratio, void* stream);
+
 /* shared_scan_* (src/simd_scan_shared.cpp:9-466): K bitvectors, predicate k's at
  * d_bitvecs + k*stride_bytes (stride a multiple of 4); d_counts[K] overwritten (may be NULL). */
 int sss_shared_scan(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo,

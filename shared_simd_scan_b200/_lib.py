@@ -36,6 +36,7 @@ SIGNATURES = {
     "sss_positions": (_i, [_vp, _vp, _u64, _u64, _vp, _u64, _vp, _vp]),
     "sss_bitvec_combine": (_i, [_vp, _i, _vp, _vp, _u64, _vp, _vp, _vp]),
     "sss_unpack_at": (_i, [_vp, _vp, _i, _vp, _u64, _vp, _vp]),
+    "sss_calibrate": (_i, [_vp, _i, _vp, _vp, _u64, _u32, _vp]),
     "sss_shared_scan": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _i, _vp, _u64, _vp, _vp]),
     "sss_shared_scan_linear": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "sss_host_unpack": (_i, [_vp, _vp, _u64, _i, _vp]),

@@ -226,6 +226,17 @@ def decompress_at(packed: torch.Tensor, w: int, positions: torch.Tensor, num: Op
     return out[:num]
 
 
+_CALIB = {"read": 0, "write": 1, "copy": 2, "mix": 3}
+
+
+def calibrate(mode: str, a: Optional[torch.Tensor], b: Optional[torch.Tensor], nbytes: int, ratio: int = 1) -> None:
+    """One streaming pass with the access mix `mode` (read / write / copy / mix = read nbytes, write
+    nbytes/ratio); the caller times it.  See sss_calibrate."""
+    ctx = Context.current()
+    check(lib().sss_calibrate(ctx.handle, _CALIB[mode], a.data_ptr() if a is not None else None,
+                              b.data_ptr() if b is not None else None, nbytes, ratio, _stream()), "sss_calibrate")
+
+
 # ---- host-buffer operators (numpy arrays or pinned CPU tensors) ------------------------------------
 
 Host = Union[np.ndarray, torch.Tensor]

@@ -1,0 +1,78 @@
+// calib.cu -- memory-bandwidth calibration kernels.
+//
+// The reference ships two host micro-benchmarks next to its scans -- bench_memory<T> (an element
+// loop copy) and bench_memcpy (src/benchmark_misc.cpp:9-52) -- to put its scan rates next to what the
+// machine's memory can do.  The counterpart here measures what a B200's HBM delivers for the access
+// MIXES of this path, because the roofline denominator (a copy: 50 % reads, 50 % writes) is not the
+// mix of a scan: the fused scan at W bits reads W bytes for every byte it writes.
+//
+//   mode READ   : stream `bytes` from a, fold them into one word (so the loads cannot be elided)
+//   mode WRITE  : stream `bytes` into b
+//   mode COPY   : a -> b, `bytes` each way            (what MEASURED_PEAKS.json's hbm_gbs measures)
+//   mode MIX    : read `bytes` from a, write bytes/ratio to b: the traffic shape of scan_range_kernel<ratio>
+//
+// Plain grid-stride kernels with 128-bit accesses, 8 independent loads in flight per thread.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sss {
+
+constexpr int kCalibUnroll = 8;
+
+__global__ void __launch_bounds__(kThreads)
+calib_kernel(int mode, const uint4* __restrict__ a, uint4* __restrict__ b, uint64_t n_vec, uint32_t ratio,
+             unsigned long long* __restrict__ sink)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+    const uint64_t t0 = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    uint32_t acc = 0;
+    if (mode == 1) {  // WRITE
+        const uint4 v = make_uint4((uint32_t)t0, 1u, 2u, 3u);
+        for (uint64_t i = t0; i < n_vec; i += stride) __stcs(b + i, v);
+    } else {
+        for (uint64_t base = t0; base < n_vec; base += stride * kCalibUnroll) {
+            uint4 v[kCalibUnroll];
+#pragma unroll
+            for (int u = 0; u < kCalibUnroll; u++) {
+                const uint64_t i = base + (uint64_t)u * stride;
+                v[u] = i < n_vec ? __ldcs(a + i) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < kCalibUnroll; u++) {
+                const uint64_t i = base + (uint64_t)u * stride;
+                if (mode == 2) {  // COPY
+                    if (i < n_vec) __stcs(b + i, v[u]);
+                } else {
+                    acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+                }
+            }
+            if (mode == 3) {
+                // MIX: this round read kCalibUnroll * stride vectors CTA-wide; every `ratio`-th of them is
+                // written back, contiguously (thread t of the round writes vector base/ratio + ...)
+                const uint64_t round_first = base - t0;                  // first vector of the round
+                const uint64_t out_first = round_first / ratio;          // (rounds are multiples of ratio: see launch)
+                const uint64_t out_count = stride * kCalibUnroll / ratio;
+                const uint64_t n_out = n_vec / ratio;
+                for (uint64_t j = t0; j < out_count && out_first + j < n_out; j += stride)
+                    __stcs(b + out_first + j, make_uint4(acc, acc, acc, acc));
+            }
+        }
+        if (acc == 0x9E3779B9u && sink != nullptr) atomicAdd(sink, 1ull);  // keeps the loads alive
+    }
+}
+
+cudaError_t launch_calibrate(const Device& dev, int mode, const void* a, void* b, uint64_t bytes, uint32_t ratio,
+                             unsigned long long* sink, cudaStream_t stream)
+{
+    const uint64_t n_vec = bytes / 16;
+    if (n_vec == 0) return cudaSuccess;
+    // grid: 8 CTAs per SM; for MIX the vectors a round covers must divide by the ratio -> round the grid
+    unsigned grid = (unsigned)dev.sm_count * 8;
+    if (mode == 3 && ratio > 1) grid = grid / ratio * ratio;
+    if (grid == 0) grid = ratio;
+    calib_kernel<<<grid, kThreads, 0, stream>>>(mode, static_cast<const uint4*>(a), static_cast<uint4*>(b), n_vec,
+                                                ratio == 0 ? 1 : ratio, sink);
+    return cudaGetLastError();
+}
+
+}  // namespace sss

@@ -333,6 +333,17 @@ int sss_unpack_at(sss_ctx* ctx, const void* d_packed, int w, const uint64_t* d_p
                                         num, d_out, static_cast<cudaStream_t>(stream)));
 }
 
+int sss_calibrate(sss_ctx* ctx, int mode, const void* d_a, void* d_b, uint64_t bytes, uint32_t ratio, void* stream)
+{
+    if (ctx == nullptr || mode < SSS_CALIB_READ || mode > SSS_CALIB_MIX) return SSS_ERR_INVALID_ARG;
+    if (mode != SSS_CALIB_WRITE && (d_a == nullptr || (reinterpret_cast<uintptr_t>(d_a) & 15))) return SSS_ERR_INVALID_ARG;
+    if (mode != SSS_CALIB_READ && (d_b == nullptr || (reinterpret_cast<uintptr_t>(d_b) & 15))) return SSS_ERR_INVALID_ARG;
+    if (mode == SSS_CALIB_MIX && (ratio == 0 || ratio > 64)) return SSS_ERR_INVALID_ARG;
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    return cuda_status(launch_calibrate(ctx->dev, mode, d_a, d_b, bytes, ratio, ctx->d_counts + SSS_MAX_PREDICATES,
+                                        static_cast<cudaStream_t>(stream)));
+}
+
 // true when the scan kernel itself adds the match counts to `d_counts` (no histogram epilogue)
 static bool counts_directly(bool, int K) { return K <= kDirectCountMaxK; }
 

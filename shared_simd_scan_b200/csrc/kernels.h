@@ -68,6 +68,10 @@ cudaError_t launch_bitvec_combine(const Device& dev, int op, const uint32_t* a, 
 cudaError_t launch_unpack_at(const Device& dev, const void* packed, int w, const unsigned long long* positions,
                              uint64_t num, int32_t* out, cudaStream_t stream);
 
+// calib.cu -- HBM bandwidth for the access mixes of this path (read / write / copy / read:write = ratio:1)
+cudaError_t launch_calibrate(const Device& dev, int mode, const void* a, void* b, uint64_t bytes, uint32_t ratio,
+                             unsigned long long* sink, cudaStream_t stream);
+
 // positions.cu -- bitvector -> ascending position list
 size_t positions_workspace_bytes(uint64_t n);
 cudaError_t launch_positions(const Device& dev, const uint32_t* bitvec, uint64_t n, uint64_t base,

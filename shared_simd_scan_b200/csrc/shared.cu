@@ -193,7 +193,8 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
 // 16 CONSECUTIVE blocks, park their words in a shared-memory stage [predicate][block], and the CTA
 // then writes every predicate's 16 words as one 64-byte run (a half-warp per predicate).
 constexpr int kWideMinK = 512;
-constexpr int kWideWarps = kSThreads / 32;   // blocks per step
+constexpr int kWideThreads = 512;
+constexpr int kWideWarps = kWideThreads / 32;  // blocks per step
 constexpr int kWideRowPad = kWideWarps + 1;  // odd pitch: conflict-free for the lane = column accesses
 static_assert(kWideWarps == 16, "the drain below maps a half-warp to a predicate's 16-word run");
 
@@ -230,7 +231,7 @@ __device__ __forceinline__ uint32_t wide_code_id(const uint32_t* blk, uint32_t j
 }
 
 template <int W, bool kSmem>
-__global__ void __launch_bounds__(kSThreads, 1)
+__global__ void __launch_bounds__(kWideThreads, 1)
 shared_scan_wide_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                         const uint8_t* __restrict__ g_index, int K, uint32_t* __restrict__ bitvecs,
                         uint64_t stride_words, bool count_matches, const IndexSmemPlan plan)
@@ -330,7 +331,7 @@ static cudaError_t launch_wide(const Device& dev, const void* packed, uint64_t n
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_wide_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(
+    shared_scan_wide_kernel<W, kSmem><<<grid, kWideThreads, smem, stream>>>(
         packed, readable, n, static_cast<const uint8_t*>(index), K, bitvecs, stride_words, count_matches, plan);
     return cudaGetLastError();
 }

@@ -441,3 +441,21 @@ def test_late_materialisation(sss, w):
     exp = B.unpack_at(packed_b, w, host(pos)[:k].astype(np.uint64))
     assert (got == exp).all()
     assert (got.astype(np.uint32) == codes_b[(codes_a >= 17) & (codes_a <= 300)]).all()
+
+
+@pytest.mark.gpu
+def test_calibration_kernels_move_the_bytes(sss):
+    """sss_calibrate: copy reproduces the source, write fills the target, mix writes bytes/ratio."""
+    nbytes = (1 << 22) + 4096
+    a = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device="cuda")
+    b = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    sss.calibrate("copy", a, b, nbytes)
+    assert torch.equal(a, b)
+    b.zero_()
+    sss.calibrate("write", None, b, nbytes)
+    assert int((b.view(torch.int32).view(-1, 4)[:, 1] == 1).sum().item()) == nbytes // 16
+    sss.calibrate("read", a, None, nbytes)
+    b.zero_()
+    sss.calibrate("mix", a, b, nbytes, 4)
+    torch.cuda.synchronize()
+    assert not b[nbytes // 4 + 64:].any()          # nothing beyond bytes/ratio is written
