@@ -281,11 +281,12 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
         ring.release_warp(iter, tile, loaded);  // the stage is free once every warp has copied its words
         if (active) {
             uint32_t id[32];
-            block_ids<W>(x, ix, id);
+            if constexpr (kSmem) block_rows<W>(x, ix, id);  // row handles directly
+        else block_ids<W>(x, ix, id);
             uint8_t* row0 = out + gb * 4 * (uint64_t)K;  // rows 4*gb .. 4*gb+3
             if (K <= kDirectCountMaxK) {
                 // per-predicate result words as in shared.cu, then bytes -> rows
-                rows_of_ids<kSmem>(ix, id);
+                if constexpr (!kSmem) rows_of_ids<kSmem>(ix, id);
                 uint32_t m[32], r[8];
 #pragma unroll
                 for (int j = 0; j < 32; j++) m[j] = row_mask_word<kSmem>(ix, id[j], 0);  // (no counter column)
@@ -310,7 +311,7 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
                         if ((uint32_t)j < tail_bits) hist.add(id[j]);
                 }
             }
-            rows_of_ids<kSmem>(ix, id);
+            if constexpr (!kSmem) rows_of_ids<kSmem>(ix, id);
             if (kSmem && count_matches) {  // the rows carry their interval's counter
                 if (!last) {
 #pragma unroll

@@ -429,6 +429,54 @@ __device__ __forceinline__ void block_ids(const uint32_t (&x)[W], const PredInde
     if (flags & kSeveralBit) BlockIds<W, 0>::fix(x, ix, id);
 }
 
+// Row handles straight from the locator (merged rows in shared memory): the id never materialises --
+// row = (bucket's id at start) * row_bytes + base, plus one row when the code passed the threshold
+// (a multiply-add and a predicated add instead of mask, add, select, multiply-add).
+template <int W, int J>
+struct BlockRows {
+    static __device__ __forceinline__ void fast(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&row)[32],
+                                                uint32_t& flags)
+    {
+        const uint32_t t = left_aligned_code<W, J>(x);
+        if constexpr (W <= kDirectMaxW) {
+            row[J] = locator_entry(ix, t >> (32 - W)) * ix.row_bytes + ix.rows_saddr;
+        } else {
+            const uint32_t e = locator_entry(ix, t >> (32 - kBucketBits));
+            uint32_t r = (e & kBucketIdMask) * ix.row_bytes + ix.rows_saddr;
+            if ((t << kBucketBits) > e) r += ix.row_bytes;
+            row[J] = r;
+            flags |= e;
+        }
+        BlockRows<W, J + 1>::fast(x, ix, row, flags);
+    }
+    static __device__ __forceinline__ void fix(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&row)[32])
+    {
+        if constexpr (W > kDirectMaxW) {
+            const uint32_t t = left_aligned_code<W, J>(x);
+            const uint32_t e = locator_entry(ix, t >> (32 - kBucketBits));
+            if (e & kSeveralBit) {
+                uint32_t i = e & kBucketIdMask;
+                while (t > ix.thr[i]) i++;
+                row[J] = i * ix.row_bytes + ix.rows_saddr;
+            }
+        }
+        BlockRows<W, J + 1>::fix(x, ix, row);
+    }
+};
+template <int W>
+struct BlockRows<W, 32> {
+    static __device__ __forceinline__ void fast(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32], uint32_t&) {}
+    static __device__ __forceinline__ void fix(const uint32_t (&)[W], const PredIndexView&, uint32_t (&)[32]) {}
+};
+
+template <int W>
+__device__ __forceinline__ void block_rows(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&row)[32])
+{
+    uint32_t flags = 0;
+    BlockRows<W, 0>::fast(x, ix, row, flags);
+    if (flags & kSeveralBit) BlockRows<W, 0>::fix(x, ix, row);
+}
+
 // interval ids -> row handles: the shared-window address of the lane's replica of the row (kSmem),
 // or the row's byte offset in the global table.  One multiply-add per code; the mask columns and the
 // match counter are then at warp-uniform offsets.

@@ -90,10 +90,11 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
         const uint32_t unrot = rot * Rot::kPieceCodes;
         const uint32_t keep = last ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
         uint32_t id[32];
-        block_ids<W>(x, ix, id);
+        if constexpr (kSmem) block_rows<W>(x, ix, id);  // row handles directly
+        else block_ids<W>(x, ix, id);
         uint32_t* p = bitvecs + gb;  // this block's word of predicate 0; += stride_words per predicate
         if (K <= kDirectCountMaxK) {  // one byte of predicates per code: the cheap 32 x 8 transpose
-            rows_of_ids<kSmem>(ix, id);
+            if constexpr (!kSmem) rows_of_ids<kSmem>(ix, id);
             uint32_t m[32], r[8];
 #pragma unroll
             for (int j = 0; j < 32; j++) m[j] = row_mask_word<kSmem>(ix, id[j], 0);  // (no counter column: K <= 8)
@@ -121,7 +122,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
                     if ((uint32_t)j < tail_bits) hist.add(id[j]);
             }
         }
-        rows_of_ids<kSmem>(ix, id);
+        if constexpr (!kSmem) rows_of_ids<kSmem>(ix, id);
         if (kSmem && count_matches) {  // the rows carry their interval's counter
             if (!last) {
 #pragma unroll
