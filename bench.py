@@ -581,10 +581,31 @@ def calibration(api, timed, peak):
     return rows
 
 
+def launch_ms(fn, warm=2, rounds=5):
+    """Duration of one launch of `fn` in ms: best of `rounds` event pairs, each around enough back-to-back
+    launches to fill about a millisecond (an event pair around ONE 50 us launch reads ~10 us too long)."""
+    import torch
+
+    def timed_once(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    reps = max(1, min(10, int(1.0 / max(timed_once(1), 1e-3))))
+    return min(timed_once(reps) for _ in range(rounds))
+
+
 def shared_sweep(args, api, columns, n, peak):
     """The metric's table: shared scan (K bitvectors + K counts) and linear-layout shared scan at EVERY
     bit width 1..32 and K in {1, 8, 64, 1024}, device-resident (same method as tools/sweep_wk.py: K
-    uniform-random ranges, 2 warm-ups, best of 5 by CUDA events).  n is halved until the output fits a
+    uniform-random ranges, 2 warm-ups, best of 5 event pairs, each around up to 10 back-to-back launches).  n is halved until the output fits a
     16 GiB arena (K = 1024: 2^27 codes).  Rows are [op, w, K, log2 n, ms, G codes/s, GB/s, fraction of
     the measured HBM peak]; bytes = n * (w/8 + K/8)."""
     import math
@@ -614,17 +635,7 @@ def shared_sweep(args, api, columns, n, peak):
                     nrows = 4 * ((n2 + 31) // 32)
                     buf = arena[: nrows * K].view(nrows, K)
                     fn = lambda: api.shared_scan_linear(columns[w], n2, w, lo_d, hi_d, out=buf, counts=cnt)  # noqa: E731
-                for _ in range(2):
-                    fn()
-                torch.cuda.synchronize()
-                best = float("inf")
-                for _ in range(5):
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record()
-                    fn()
-                    b.record()
-                    b.synchronize()
-                    best = min(best, a.elapsed_time(b))
+                best = launch_ms(fn)
                 nbytes = n2 * (w / 8 + K / 8)
                 rows.append([op, w, K, int(math.log2(n2)), round(best, 4), round(n2 / best / 1e6, 1),
                              round(nbytes / best / 1e6, 1), round(nbytes / best / 1e6 / peak, 4)])

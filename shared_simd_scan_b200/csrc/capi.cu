@@ -365,6 +365,9 @@ static int shared_scan_body(sss_ctx* ctx, bool linear, const void* d_packed, uin
                             uint64_t stride_bytes, unsigned long long* d_counts, cudaStream_t st)
 {
     if (n == 0) return SSS_OK;
+    if (K <= kNarrowMaxK && w <= kNarrowMaxW)  // few predicates over narrow codes: group-table kernel
+        return cuda_status(launch_shared_scan_narrow(ctx->dev, d_packed, n, w, ctx->d_index, K, d_out, stride_bytes / 4,
+                                                     linear, d_counts, st));
     if (linear)
         return cuda_status(launch_shared_scan_linear(ctx->dev, d_packed, n, w, ctx->d_index, K,
                                                      static_cast<uint8_t*>(d_out), d_counts, d_counts != nullptr, st));

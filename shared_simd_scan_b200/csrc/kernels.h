@@ -51,6 +51,15 @@ cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n
                                uint32_t* bitvecs, uint64_t stride_words, unsigned long long* counts, bool count_matches,
                                cudaStream_t stream);
 
+// narrow.cu -- K <= kNarrowMaxK predicates over codes of at most kNarrowMaxW bits, either output layout:
+// a table indexed by a GROUP of adjacent codes replaces the per-code interval lookup.  Adds the match
+// counts to counts[0..K) itself (may be null).
+constexpr int kNarrowMaxK = 8;
+constexpr int kNarrowMaxW = 6;
+cudaError_t launch_shared_scan_narrow(const Device& dev, const void* packed, uint64_t n, int w, const void* index,
+                                      int K, void* out, uint64_t stride_words, bool linear,
+                                      unsigned long long* counts, cudaStream_t stream);
+
 // linear.cu -- K predicates in one pass -> [4*ceil(n/32)][K] byte matrix
 cudaError_t launch_shared_scan_linear(const Device& dev, const void* packed, uint64_t n, int w, const void* index,
                                       int K, uint8_t* out, unsigned long long* counts, bool count_matches,

@@ -106,46 +106,6 @@ __device__ __forceinline__ void store_row_piece(uint8_t* dst, const uint32_t (&w
     }
 }
 
-// 4 x 4 byte transpose: in a,b,c,d = four predicates' result words (byte g = codes 8g..8g+7);
-// out o[g] = bytes (a.g, b.g, c.g, d.g) = four consecutive predicate bytes of row g
-__device__ __forceinline__ void byte_transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t (&o)[4])
-{
-    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(c, d, 0x5140);
-    const uint32_t t2 = __byte_perm(a, b, 0x7362), t3 = __byte_perm(c, d, 0x7362);
-    o[0] = __byte_perm(t0, t1, 0x5410);
-    o[1] = __byte_perm(t0, t1, 0x7632);
-    o[2] = __byte_perm(t2, t3, 0x5410);
-    o[3] = __byte_perm(t2, t3, 0x7632);
-}
-
-// The 4 rows x K bytes of a block for K <= 8, from the per-predicate result words r[k] (bit j = code j):
-// the rows of a block are contiguous (4K bytes), so K = 1, 2, 4, 8 are ONE 4/8/16/32-byte store.
-__device__ __forceinline__ void store_block_small(uint8_t* dst, const uint32_t (&r)[8], int K)
-{
-    uint32_t lo[4], hi[4];
-    byte_transpose4(r[0], r[1], r[2], r[3], lo);
-    if (K == 1 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
-        __stcs(reinterpret_cast<uint32_t*>(dst), r[0]);
-    } else if (K == 2 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-        __stcs(reinterpret_cast<uint2*>(dst),
-               make_uint2(__byte_perm(lo[0], lo[1], 0x5410), __byte_perm(lo[2], lo[3], 0x5410)));
-    } else if (K == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        __stcs(reinterpret_cast<uint4*>(dst), make_uint4(lo[0], lo[1], lo[2], lo[3]));
-    } else {
-        byte_transpose4(r[4], r[5], r[6], r[7], hi);
-        if (K == 8 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
-            const uint32_t ws[8] = {lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], lo[3], hi[3]};
-            st_v8_u32(dst, ws);
-        } else {
-#pragma unroll
-            for (int g = 0; g < 4; g++)
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    if (k < K) dst[g * K + k] = (uint8_t)((k < 4 ? lo[g] : hi[g]) >> (8 * (k & 3)));
-        }
-    }
-}
-
 // interval id of code `j` (runtime) of a block whose W words start at `blk` in shared memory
 template <int W>
 __device__ __forceinline__ uint32_t code_id_runtime(const uint32_t* blk, uint32_t j, const PredIndexView& ix)

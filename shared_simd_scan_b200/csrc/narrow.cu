@@ -1,0 +1,235 @@
+// narrow.cu -- shared scans with at most 8 predicates over NARROW codes (W <= 6), both output layouts.
+//
+// The index-driven kernels (shared.cu, linear.cu) spend ~12 instructions per code at K <= 8: extract
+// the code, look up its interval, look up the interval's mask row.  That is right for wide codes, but
+// a column of 1..6-bit codes has a roofline of 1.1-1.8 bytes per code, i.e. 3.6-5.8 T codes/s, which
+// 12 instructions per code cannot reach (issue-bound at ~2 T codes/s; profiles/r01_ncu_v3_shared_w5_k8.txt).
+// For narrow codes the answer does not need an interval at all: a group of G adjacent codes (G * W <=
+// 12 bits) indexes a table that holds the G codes' 8-bit match masks in one 32-bit entry -- one
+// lookup per G codes instead of two per code.  Every CTA derives that table in its prologue from the
+// predicate index of the call (direct locator + mask rows, predindex.cuh) and keeps up to 32
+// lane-private replicas of it in shared memory (no bank conflicts).  The entries' bytes are brought
+// into the 32 x 8 transpose's input order with 16 PRMTs; from there on it is the K <= 8 path of the
+// other kernels: three bit stages, popcount for the counts, per-predicate result words (bitvectors) or
+// the block's 4K bytes in one store (linear layout).
+//
+// Replaces, for this corner, the same reference functions as shared.cu / linear.cu
+// (src/simd_scan_shared.cpp:34-151, src/simd_scan_shared_linear.cpp:9-82).
+// Roofline: HBM.  Algorithmic bytes per code = W/8 + K/8.
+#include <array>
+#include <utility>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "predindex.cuh"
+
+namespace sss {
+
+constexpr int kNThreads = 512;
+#ifndef SSS_NARROW_CTAS
+#define SSS_NARROW_CTAS 1  // CTAs per SM (2 measured no better: the kernel is bound by its 8 write streams)
+#endif
+constexpr int kNCtasPerSm = SSS_NARROW_CTAS;
+static_assert(kNarrowMaxK == kDirectCountMaxK, "the narrow path counts by popcount");
+
+template <int W>
+struct NarrowCfg {
+    static constexpr int kG = W <= 3 ? 4 : 2;  // codes per lookup
+    static constexpr int kBits = kG * W;       // index bits
+    static constexpr int kEntries = 1 << kBits;
+    static constexpr int kLookups = 32 / kG;
+    // blocks per thread per tile: a block of narrow codes is only W words, and a tile has to be large
+    // enough (>= 16 KB) for the ring's per-tile bookkeeping to disappear behind the work
+    static constexpr int kBT = 8 / W > 1 ? 8 / W : 1;
+    static constexpr int kBlocksPerTile = kNThreads * kBT;
+    static constexpr int kTileBytes = kBlocksPerTile * W * 4;
+    static constexpr int kStages = 4;
+    using Ring = TileRing<kTileBytes, kStages>;
+    static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
+    static_assert(kBits <= 12, "group index must stay small enough to replicate");
+};
+
+inline int narrow_rep_log2(size_t ring_bytes, int entries)
+{
+    int r = 5;
+    while (r > 0 && ring_bytes + ((size_t)entries * 4 << r) + 64 > (size_t)(224 / kNCtasPerSm - 4) * 1024) r--;
+    return r;
+}
+
+// group g of the block: G adjacent codes = kBits bits at bit offset g * kBits of the W words
+template <int W, int G>
+__device__ __forceinline__ uint32_t group_index(const uint32_t (&x)[W])
+{
+    using Cfg = NarrowCfg<W>;
+    constexpr int bit = G * Cfg::kBits, wi = bit >> 5, sh = bit & 31;
+    constexpr uint32_t mask = (1u << Cfg::kBits) - 1u;
+    if constexpr (sh + Cfg::kBits <= 32) {
+        return (x[wi] >> sh) & mask;
+    } else {
+        return __funnelshift_r(x[wi], x[wi + 1 < W ? wi + 1 : wi], sh) & mask;
+    }
+}
+
+template <int W, int G>
+struct GroupLookups {
+    static __device__ __forceinline__ void run(const uint32_t (&x)[W], uint32_t base, uint32_t stride,
+                                               uint32_t (&e)[NarrowCfg<W>::kLookups])
+    {
+        asm("ld.shared.u32 %0, [%1];" : "=r"(e[G]) : "r"(group_index<W, G>(x) * stride + base));
+        GroupLookups<W, G + 1>::run(x, base, stride, e);
+    }
+};
+template <int W>
+struct GroupLookups<W, NarrowCfg<W>::kLookups> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[W], uint32_t, uint32_t,
+                                               uint32_t (&)[NarrowCfg<W>::kLookups])
+    {
+    }
+};
+
+template <int W>
+__global__ void __launch_bounds__(kNThreads, kNCtasPerSm)
+shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
+                          const uint8_t* __restrict__ g_index, int K, void* __restrict__ out, uint64_t stride_words,
+                          bool linear, unsigned long long* __restrict__ counts, int rep_log2)
+{
+    using Cfg = NarrowCfg<W>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    // ---- prologue: the group table, `R` replicas interleaved entry by entry --------------------------
+    {
+        const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(g_index + PredIndexLayout::kHeader);
+        const uint16_t* lut = reinterpret_cast<const uint16_t*>(g_index + PredIndexLayout::kLocator);  // W <= 13: direct
+        const uint32_t* masks = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kMasks);
+        const uint32_t row_words = h->row_words;
+        uint32_t* table = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);
+        for (uint32_t i = threadIdx.x; i < ((uint32_t)Cfg::kEntries << rep_log2); i += kNThreads) {
+            const uint32_t v = i >> rep_log2;
+            uint32_t entry = 0;
+#pragma unroll
+            for (int c = 0; c < Cfg::kG; c++) {
+                const uint32_t code = (v >> (c * W)) & code_mask(W);
+                entry |= (masks[(uint32_t)lut[code] * row_words] & 0xFFu) << (8 * c);
+            }
+            table[i] = entry;
+        }
+    }
+    const uint32_t R = 1u << rep_log2;
+    const uint32_t table_base = smem_u32(smem + Cfg::kRingBytes) + ((threadIdx.x & (R - 1)) << 2);
+    const uint32_t table_stride = 4u << rep_log2;
+    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    ring.start();  // contains the __syncthreads that publishes the table
+
+    const uint64_t n_blocks = (n + 31) >> 5;
+    const uint32_t tail_bits = (uint32_t)(n & 31);
+    uint32_t direct[kNarrowMaxK] = {};
+
+    uint32_t iter = 0;
+    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
+        ring.wait(iter);
+        const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
+        // thread t owns blocks t, t + 512, ... of the tile (lanes stay adjacent: conflict-free loads,
+        // coalesced stores)
+        uint32_t x[Cfg::kBT][W];
+        uint32_t loaded = 0;
+#pragma unroll
+        for (int u = 0; u < Cfg::kBT; u++) {
+            load_block<W, 1>(buf, u * kNThreads + threadIdx.x, x[u], 0u);
+#pragma unroll
+            for (int k = 0; k < W; k++) loaded |= x[u][k];
+        }
+        ring.release_warp(iter, tile, loaded);
+#pragma unroll
+        for (int u = 0; u < Cfg::kBT; u++) {
+            const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + u * kNThreads + threadIdx.x;
+            if (gb >= n_blocks) break;
+            const uint32_t keep = (tail_bits != 0 && gb == n_blocks - 1) ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
+
+            uint32_t e[Cfg::kLookups];
+            GroupLookups<W, 0>::run(x[u], table_base, table_stride, e);
+            // entries -> r[q] byte b = the predicate bits of code 8b + q (the 32 x 8 transpose's input order)
+            uint32_t r[8];
+            if constexpr (Cfg::kG == 4) {  // e[g] bytes = codes 4g .. 4g+3
+                uint32_t o[4];
+                byte_transpose4(e[0], e[2], e[4], e[6], o);
+                r[0] = o[0]; r[1] = o[1]; r[2] = o[2]; r[3] = o[3];
+                byte_transpose4(e[1], e[3], e[5], e[7], o);
+                r[4] = o[0]; r[5] = o[1]; r[6] = o[2]; r[7] = o[3];
+            } else {  // e[g] bytes 0, 1 = codes 2g, 2g+1
+#pragma unroll
+                for (int hq = 0; hq < 4; hq++) {
+                    const uint32_t t0 = __byte_perm(e[hq], e[4 + hq], 0x5140);
+                    const uint32_t t1 = __byte_perm(e[8 + hq], e[12 + hq], 0x5140);
+                    r[2 * hq] = __byte_perm(t0, t1, 0x5410);
+                    r[2 * hq + 1] = __byte_perm(t0, t1, 0x7632);
+                }
+            }
+            transpose_bits_32x8(r);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                r[k] &= keep;
+                if (k < K) direct[k] += __popc(r[k]);
+            }
+            if (linear) {
+                store_block_small(static_cast<uint8_t*>(out) + gb * 4 * (uint64_t)K, r, K);
+            } else {
+                uint32_t* p = static_cast<uint32_t*>(out) + gb;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (k < K) st_stream_u32(p, r[k]);
+                    p += stride_words;
+                }
+            }
+        }
+    }
+    if (counts != nullptr) {
+#pragma unroll
+        for (int k = 0; k < kNarrowMaxK; k++) {
+            const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, direct[k]);
+            if ((threadIdx.x & 31) == 0 && k < K && s != 0) atomicAdd(&counts[k], (unsigned long long)s);
+        }
+    }
+}
+
+template <int W>
+static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K, void* out,
+                            uint64_t stride_words, bool linear, unsigned long long* counts, cudaStream_t stream)
+{
+    using Cfg = NarrowCfg<W>;
+    const int r = narrow_rep_log2(Cfg::kRingBytes, Cfg::kEntries);
+    const size_t smem = Cfg::kRingBytes + ((size_t)Cfg::kEntries * 4 << r) + 64;
+    static size_t configured[64] = {};
+    if (configured[dev.ordinal & 63] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(shared_scan_narrow_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev.ordinal & 63] = smem;
+    }
+    const uint64_t n_blocks = (n + 31) / 32;
+    const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
+    const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
+    const uint64_t max_ctas = (uint64_t)dev.sm_count * kNCtasPerSm;
+    const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
+    shared_scan_narrow_kernel<W><<<grid, kNThreads, smem, stream>>>(packed, readable, n,
+                                                                     static_cast<const uint8_t*>(index), K, out,
+                                                                     stride_words, linear, counts, r);
+    return cudaGetLastError();
+}
+
+using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, void*, uint64_t, bool,
+                                 unsigned long long*, cudaStream_t);
+
+template <int... Ws>
+static constexpr auto make_table(std::integer_sequence<int, Ws...>)
+{
+    return std::array<Launcher, sizeof...(Ws)>{&launch_w<Ws + 1>...};
+}
+
+cudaError_t launch_shared_scan_narrow(const Device& dev, const void* packed, uint64_t n, int w, const void* index,
+                                      int K, void* out, uint64_t stride_words, bool linear,
+                                      unsigned long long* counts, cudaStream_t stream)
+{
+    static constexpr auto table = make_table(std::make_integer_sequence<int, kNarrowMaxW>{});
+    return table[w - 1](dev, packed, n, index, K, out, stride_words, linear, counts, stream);
+}
+
+}  // namespace sss

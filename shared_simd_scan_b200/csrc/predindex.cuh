@@ -561,14 +561,11 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32])
 // in : m[j] bits 0..7 = the predicates on code j.   out: r[k] bit j = predicate k on code j.
 // Four codes are packed per word so that byte b of word q is code 8b + q; the three bit stages then
 // leave predicate k's 32 results in word k already in code order -- 72 ops instead of 256.
-__device__ __forceinline__ void transpose32x8(const uint32_t (&m)[32], uint32_t (&r)[8])
+
+// bit stages of the 32 x 8 transpose.  in: r[q] byte b = the 8 predicate bits of code 8b + q;
+// out: r[k] bit j = predicate k on code j
+__device__ __forceinline__ void transpose_bits_32x8(uint32_t (&r)[8])
 {
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const uint32_t lo = __byte_perm(m[q], m[q + 8], 0x0040);        // m[q].b0, m[q+8].b0
-        const uint32_t hi = __byte_perm(m[q + 16], m[q + 24], 0x0040);  // m[q+16].b0, m[q+24].b0
-        r[q] = __byte_perm(lo, hi, 0x5410);
-    }
 #pragma unroll
     for (int k = 0; k < 4; k++) exchange_bits<4>(r[k], r[k + 4]);
 #pragma unroll
@@ -577,6 +574,58 @@ __device__ __forceinline__ void transpose32x8(const uint32_t (&m)[32], uint32_t 
         for (int k = g; k < g + 2; k++) exchange_bits<2>(r[k], r[k + 2]);
 #pragma unroll
     for (int k = 0; k < 8; k += 2) exchange_bits<1>(r[k], r[k + 1]);
+}
+
+__device__ __forceinline__ void transpose32x8(const uint32_t (&m)[32], uint32_t (&r)[8])
+{
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const uint32_t lo = __byte_perm(m[q], m[q + 8], 0x0040);        // m[q].b0, m[q+8].b0
+        const uint32_t hi = __byte_perm(m[q + 16], m[q + 24], 0x0040);  // m[q+16].b0, m[q+24].b0
+        r[q] = __byte_perm(lo, hi, 0x5410);
+    }
+    transpose_bits_32x8(r);
+}
+
+// ---- linear layout, up to 8 predicates ----------------------------------------------------------------
+// 4 x 4 byte transpose: in a,b,c,d = four predicates' result words (byte g = codes 8g..8g+7);
+// out o[g] = bytes (a.g, b.g, c.g, d.g) = four consecutive predicate bytes of row g
+__device__ __forceinline__ void byte_transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t (&o)[4])
+{
+    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(c, d, 0x5140);
+    const uint32_t t2 = __byte_perm(a, b, 0x7362), t3 = __byte_perm(c, d, 0x7362);
+    o[0] = __byte_perm(t0, t1, 0x5410);
+    o[1] = __byte_perm(t0, t1, 0x7632);
+    o[2] = __byte_perm(t2, t3, 0x5410);
+    o[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+// The 4 rows x K bytes of a block for K <= 8, from the per-predicate result words r[k] (bit j = code j):
+// the rows of a block are contiguous (4K bytes), so K = 1, 2, 4, 8 are ONE 4/8/16/32-byte store.
+__device__ __forceinline__ void store_block_small(uint8_t* dst, const uint32_t (&r)[8], int K)
+{
+    uint32_t lo[4], hi[4];
+    byte_transpose4(r[0], r[1], r[2], r[3], lo);
+    if (K == 1 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+        __stcs(reinterpret_cast<uint32_t*>(dst), r[0]);
+    } else if (K == 2 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+        __stcs(reinterpret_cast<uint2*>(dst),
+               make_uint2(__byte_perm(lo[0], lo[1], 0x5410), __byte_perm(lo[2], lo[3], 0x5410)));
+    } else if (K == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        __stcs(reinterpret_cast<uint4*>(dst), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+    } else {
+        byte_transpose4(r[4], r[5], r[6], r[7], hi);
+        if (K == 8 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+            const uint32_t ws[8] = {lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], lo[3], hi[3]};
+            st_v8_u32(dst, ws);
+        } else {
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (k < K) dst[g * K + k] = (uint8_t)((k < 4 ? lo[g] : hi[g]) >> (8 * (k & 3)));
+        }
+    }
 }
 
 }  // namespace sss

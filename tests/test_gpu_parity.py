@@ -311,10 +311,11 @@ def test_many_predicates(sss, w, K):
     assert (host(cnt).astype(np.uint64) == ecnt).all()
 
 
-@pytest.mark.parametrize("w", [2, 8, 13, 20, 24, 28])
-@pytest.mark.parametrize("K", [2, 16, 100, 128, 512])
+@pytest.mark.parametrize("w", [2, 3, 4, 6, 8, 13, 20, 24, 28])
+@pytest.mark.parametrize("K", [2, 7, 16, 100, 128, 512])
 def test_shared_scan_store_paths_and_row_tables(sss, w, K):
-    """Widths with rotated block loads (8, 24), 64-bit (2 mod 4) and 128-bit (4 mod 8) block loads, and
+    """Narrow codes with few predicates (the group-table kernel: W <= 6, K <= 8), widths with rotated
+    block loads (8, 24), 64-bit (2 mod 4) and 128-bit (4 mod 8) block loads, and
     predicate counts that exercise the single-store rows (K = 2), 16-byte row pieces (K = 16), ragged
     columns (K = 100) and partially replicated row tables (K = 128, 512), over several tiles."""
     n = 40_003

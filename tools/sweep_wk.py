@@ -6,7 +6,8 @@ shared scan at EVERY bit width 1..32 and K in {1, 8, 64, 1024}, device-resident,
 
 n is 2^logn codes, reduced per K so that the output stays below --max-out-gib (K = 1024 at 2^30 codes
 would be 128 GiB).  Bounds: K uniform-random ranges, lo uniform, width uniform in [0, 2*2^w/K)
-(SURVEY.md section 8 d).  Times: CUDA events, 2 warm-ups, best and median of 5.  Prints one JSON row
+(SURVEY.md section 8 d).  Times: CUDA events around up to 10 back-to-back launches, 2 warm-ups, best and
+median of 5 pairs.  Prints one JSON row
 per (op, w, K) and a per-K summary (min / median / max fraction of the measured HBM peak)."""
 import argparse
 import json
@@ -26,18 +27,23 @@ except Exception:
     pass
 
 
-def timeit(fn, reps=5, warm=2):
+def timeit(fn, rounds=5, warm=2):
+    """ms per launch: event pairs around enough back-to-back launches to fill about a millisecond (an
+    event pair around ONE 50 us launch reads ~10 us too long); best and median of `rounds` pairs."""
+    def once(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    ts = []
-    for _ in range(reps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        fn()
-        b.record()
-        b.synchronize()
-        ts.append(a.elapsed_time(b))
+    reps = max(1, min(10, int(1.0 / max(once(1), 1e-3))))
+    ts = [once(reps) for _ in range(rounds)]
     return min(ts), statistics.median(ts)
 
 
