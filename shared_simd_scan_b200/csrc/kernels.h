@@ -55,7 +55,7 @@ cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n
 // a table indexed by a GROUP of adjacent codes replaces the per-code interval lookup.  Adds the match
 // counts to counts[0..K) itself (may be null).
 constexpr int kNarrowMaxK = 8;
-constexpr int kNarrowMaxW = 6;
+constexpr int kNarrowMaxW = 13;  // == the direct-locator widths (predindex.cuh kDirectMaxW)
 cudaError_t launch_shared_scan_narrow(const Device& dev, const void* packed, uint64_t n, int w, const void* index,
                                       int K, void* out, uint64_t stride_words, bool linear,
                                       unsigned long long* counts, cudaStream_t stream);

@@ -1,12 +1,12 @@
-// narrow.cu -- shared scans with at most 8 predicates over NARROW codes (W <= 6), both output layouts.
+// narrow.cu -- shared scans with at most 8 predicates over NARROW codes (W <= 13), both output layouts.
 //
 // The index-driven kernels (shared.cu, linear.cu) spend ~12 instructions per code at K <= 8: extract
 // the code, look up its interval, look up the interval's mask row.  That is right for wide codes, but
 // a column of 1..6-bit codes has a roofline of 1.1-1.8 bytes per code, i.e. 3.6-5.8 T codes/s, which
 // 12 instructions per code cannot reach (issue-bound at ~2 T codes/s; profiles/r01_ncu_v3_shared_w5_k8.txt).
 // For narrow codes the answer does not need an interval at all: a group of G adjacent codes (G * W <=
-// 12 bits) indexes a table that holds the G codes' 8-bit match masks in one 32-bit entry -- one
-// lookup per G codes instead of two per code.  Every CTA derives that table in its prologue from the
+// 12 bits; G = 4, 2, 1 for W <= 3, <= 6, <= 13) indexes a table that holds the G codes' 8-bit match
+// masks in one 32-bit entry -- one lookup per G codes instead of two per code.  Every CTA derives that table in its prologue from the
 // predicate index of the call (direct locator + mask rows, predindex.cuh) and keeps up to 32
 // lane-private replicas of it in shared memory (no bank conflicts).  The entries' bytes are brought
 // into the 32 x 8 transpose's input order with 16 PRMTs; from there on it is the K <= 8 path of the
@@ -34,7 +34,7 @@ static_assert(kNarrowMaxK == kDirectCountMaxK, "the narrow path counts by popcou
 
 template <int W>
 struct NarrowCfg {
-    static constexpr int kG = W <= 3 ? 4 : 2;  // codes per lookup
+    static constexpr int kG = W <= 3 ? 4 : (W <= 6 ? 2 : 1);  // codes per lookup
     static constexpr int kBits = kG * W;       // index bits
     static constexpr int kEntries = 1 << kBits;
     static constexpr int kLookups = 32 / kG;
@@ -46,7 +46,7 @@ struct NarrowCfg {
     static constexpr int kStages = 4;
     using Ring = TileRing<kTileBytes, kStages>;
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
-    static_assert(kBits <= 12, "group index must stay small enough to replicate");
+    static_assert(kBits <= 13, "group index must stay small enough to replicate");
 };
 
 inline int narrow_rep_log2(size_t ring_bytes, int entries)
@@ -119,6 +119,8 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();  // contains the __syncthreads that publishes the table
 
+    using Rot = BlockRot<W, 1>;
+    const uint32_t lane_rot = Rot::lane_rot();
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
     uint32_t direct[kNarrowMaxK] = {};
@@ -133,7 +135,9 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
         uint32_t loaded = 0;
 #pragma unroll
         for (int u = 0; u < Cfg::kBT; u++) {
-            load_block<W, 1>(buf, u * kNThreads + threadIdx.x, x[u], 0u);
+            // (W = 8 reads its block rotated by lane_rot pieces, see BlockRot; undone on the result words.
+            //  The column's ragged last block may come out rotated too: its `keep` mask is applied after.)
+            load_block<W, 1>(buf, u * kNThreads + threadIdx.x, x[u], lane_rot);
 #pragma unroll
             for (int k = 0; k < W; k++) loaded |= x[u][k];
         }
@@ -154,6 +158,8 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
                 r[0] = o[0]; r[1] = o[1]; r[2] = o[2]; r[3] = o[3];
                 byte_transpose4(e[1], e[3], e[5], e[7], o);
                 r[4] = o[0]; r[5] = o[1]; r[6] = o[2]; r[7] = o[3];
+            } else if constexpr (Cfg::kG == 1) {  // e[j] = the mask of code j: the plain 32 x 8 transpose
+                transpose32x8(e, r);
             } else {  // e[g] bytes 0, 1 = codes 2g, 2g+1
 #pragma unroll
                 for (int hq = 0; hq < 4; hq++) {
@@ -163,9 +169,10 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
                     r[2 * hq + 1] = __byte_perm(t0, t1, 0x7632);
                 }
             }
-            transpose_bits_32x8(r);
+            if constexpr (Cfg::kG != 1) transpose_bits_32x8(r);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
+                if constexpr (Rot::kRot) r[k] = __funnelshift_l(r[k], r[k], lane_rot * Rot::kPieceCodes);
                 r[k] &= keep;
                 if (k < K) direct[k] += __popc(r[k]);
             }
