@@ -1,10 +1,19 @@
 #!/usr/bin/env python
-"""Print a tools/sweep_wk.py result as a w x K table (fraction of the measured HBM peak / G codes/s);
+"""Print a tools/sweep_wk.py result (or the shared_sweep table of a bench.py line) as a w x K table (fraction of the measured HBM peak / G codes/s);
 with two files, the second is shown next to the first."""
 import json
 import sys
 
-files = [json.load(open(f)) for f in sys.argv[1:]]
+def load(path):
+    """tools/sweep_wk.py output, or a bench.py line (its `shared_sweep` table)"""
+    d = json.loads(open(path).read())
+    if "shared_sweep" in d:
+        cols = d["shared_sweep"]["columns"]
+        return {"rows": [dict(zip(cols, r)) for r in d["shared_sweep"]["rows"]]}
+    return d
+
+
+files = [load(f) for f in sys.argv[1:]]
 ops = sorted({r["op"] for d in files for r in d["rows"]})
 for op in ops:
     ks = sorted({r["K"] for d in files for r in d["rows"] if r["op"] == op})
