@@ -282,7 +282,40 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
                         if ((uint32_t)j < tail_bits) row_count(id[j]);
                 }
             }
-            const uint32_t row_rot = rot * (Rot::kPieceCodes / 8);  // register row i is output row (i + row_rot) & 3
+            // Row spreading.  A thread's four rows are 32-byte pieces at a 4K-byte block stride; when all
+            // lanes of a store instruction write the SAME row of their blocks, its 32 sectors land on one
+            // offset modulo the stride and the launch loses a quarter of its speed (measured: the widths
+            // whose rotated block loads happen to permute the rows over all four positions, 16 and 32
+            // bit, ran 27 % faster than with the permutation switched off).  So every lane rotates its
+            // 32 row handles by `extra` rows (8 codes each; the order of a block's codes is free until
+            // the store) such that, together with the load rotation, lanes l, l+1, l+2, l+3 sit on four
+            // different rows: two conditional-move stages, 2 instructions per code.
+            constexpr int kLoadWays = Rot::kRot ? (Rot::kPieces >= 4 ? 4 : Rot::kPieces) : 1;  // rows the load rotation spreads over
+            uint32_t extra = 0;
+            if constexpr (kLoadWays < 4) {
+                extra = last ? 0u : ((threadIdx.x & 31u) & (uint32_t)(4 / kLoadWays - 1));
+                if (extra & 1u) {  // rotate by one row: position j takes the handle of position j + 8
+                    uint32_t t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) t[j] = id[j];
+#pragma unroll
+                    for (int j = 0; j < 24; j++) id[j] = id[j + 8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) id[24 + j] = t[j];
+                }
+                if constexpr (kLoadWays == 1) {
+                    if (extra & 2u) {  // rotate by two rows
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const uint32_t t = id[j];
+                            id[j] = id[j + 16];
+                            id[j + 16] = t;
+                        }
+                    }
+                }
+            }
+            // register row i is output row (i + row_rot) & 3
+            const uint32_t row_rot = rot * (Rot::kPieceCodes / 8) + extra;
             for (int c = 0; c < cols; c++) {
                 uint32_t m[32];
                 // derived from the kernel parameter so that it stays in a uniform register: LDS [R + UR]
@@ -299,7 +332,11 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
                 const int kk = K - 32 * c;  // predicates in this column
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const uint32_t orow = Rot::kRot ? ((i + row_rot) & 3u) : (uint32_t)i;
+#ifdef SSS_EXPERIMENT_NO_ROW_PERMUTE  // timing experiment only (wrong results): rows leave in register order
+                    const uint32_t orow = (uint32_t)i;
+#else
+                    const uint32_t orow = (i + row_rot) & 3u;
+#endif
                     uint8_t* dst = row0 + (uint64_t)orow * K + 32 * c;
                     // word q of the row = m[8i + 4*(q&1) + (q>>1)]
                     const uint32_t ws[8] = {m[8 * i + 0], m[8 * i + 4], m[8 * i + 1], m[8 * i + 5],

@@ -20,15 +20,22 @@ namespace sss {
 template <int W>
 struct UnpackCfg {
     static constexpr int kCodesPerThread = 8;                                // one 32-byte (256-bit) store per lane
-    static constexpr int kR = 4;                                             // 8-code groups per thread per tile
+#ifndef SSS_UNPACK_MIN_TILE_KB
+#define SSS_UNPACK_MIN_TILE_KB 1
+#endif
+    // 8-code groups per thread per tile: 4, more at narrow widths so that a tile stays >= MIN_TILE_KB
+    static constexpr int kR = (W * 4 >= SSS_UNPACK_MIN_TILE_KB * 4) ? 4 : (SSS_UNPACK_MIN_TILE_KB * 4 + W - 1) / W;
     static constexpr int kCodesPerTile = kThreads * kCodesPerThread * kR;    // 8192
     static constexpr int kTileBytes = kCodesPerTile / 32 * W * 4;            // 1 KB * W
     static constexpr int kStages = ring_stages(kTileBytes);
     using Ring = TileRing<kTileBytes, kStages>;
 };
 
+#ifndef SSS_UNPACK_CTAS
+#define SSS_UNPACK_CTAS 2
+#endif
 template <int W>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, SSS_UNPACK_CTAS)
 unpack_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n, int32_t* __restrict__ out)
 {
     using Cfg = UnpackCfg<W>;
@@ -57,7 +64,12 @@ unpack_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64
                     v[e] = __funnelshift_r(buf[wi], buf[wi + 1], bit & 31) & mask;
                 }
                 if (g0 + 8 <= n) {
+#ifdef SSS_UNPACK_ST128
+                    __stcs(reinterpret_cast<uint4*>(out + g0), make_uint4(v[0], v[1], v[2], v[3]));
+                    __stcs(reinterpret_cast<uint4*>(out + g0) + 1, make_uint4(v[4], v[5], v[6], v[7]));
+#else
                     st_v8_u32(out + g0, v);
+#endif
                 } else {
                     for (int e = 0; e < 8 && g0 + e < n; e++) out[g0 + e] = (int32_t)v[e];
                 }
@@ -80,7 +92,7 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, i
     }
     const uint64_t readable = round_up_u64(packed_payload_bytes(n, W), 16);
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
-    const uint64_t max_ctas = (uint64_t)dev.sm_count * 2;
+    const uint64_t max_ctas = (uint64_t)dev.sm_count * SSS_UNPACK_CTAS;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     unpack_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, out);
     return cudaGetLastError();
