@@ -278,7 +278,7 @@ def run_cfg5(args):
     lo = torch.randint(0, m + 1, (K,), generator=g)
     hi = torch.clamp(lo + torch.randint(0, 2 * (m + 1) // K, (K,), generator=g), max=m)
     lo_d, hi_d = lo.to(torch.int32).cuda(), hi.to(torch.int32).cuda()
-    out = torch.empty((K, (api.bitvec_bytes(shard.count) + 15) // 16 * 16), dtype=torch.uint8, device="cuda")
+    out = torch.empty((K, (api.bitvec_bytes(shard.count) + 127) // 128 * 128), dtype=torch.uint8, device="cuda")
     counts = torch.empty(K, dtype=torch.int64, device="cuda")
 
     def step():
@@ -513,7 +513,7 @@ def extras(args, api, columns, n, peak):
         lo_d, hi_d = lo.to(torch.int32).cuda(), hi.to(torch.int32).cuda()
         cnt = torch.empty(K, dtype=torch.int64, device="cuda")
         if kind == "shared":
-            buf = torch.empty((K, (api.bitvec_bytes(nn) + 15) // 16 * 16), dtype=torch.uint8, device="cuda")
+            buf = torch.empty((K, (api.bitvec_bytes(nn) + 127) // 128 * 128), dtype=torch.uint8, device="cuda")
             ms = timed(lambda: api.shared_scan(columns[w], nn, w, lo_d, hi_d, out=buf, counts=cnt))
         else:
             buf = torch.empty((4 * ((nn + 31) // 32), K), dtype=torch.uint8, device="cuda")
@@ -628,7 +628,7 @@ def shared_sweep(args, api, columns, n, peak):
             cnt = torch.empty(K, dtype=torch.int64, device="cuda")
             for op in ("shared", "linear"):
                 if op == "shared":
-                    stride = (api.bitvec_bytes(n2) + 31) // 32 * 32
+                    stride = (api.bitvec_bytes(n2) + 127) // 128 * 128
                     buf = arena[: K * stride].view(K, stride)
                     fn = lambda: api.shared_scan(columns[w], n2, w, lo_d, hi_d, out=buf, counts=cnt)  # noqa: E731
                 else:

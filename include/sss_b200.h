@@ -128,7 +128,8 @@ int sss_unpack_at(sss_ctx* ctx, const void* d_packed, int w, const uint64_t* d_p
 int sss_calibrate(sss_ctx* ctx, int mode, const void* d_a, void* d_b, uint64_t bytes, uint32_t ratio, void* stream);
 
 /* shared_scan_* (src/simd_scan_shared.cpp:9-466): K bitvectors, predicate k's at
- * d_bitvecs + k*stride_bytes (stride a multiple of 4); d_counts[K] overwritten (may be NULL). */
+ * d_bitvecs + k*stride_bytes (stride a multiple of 4; a 128-byte aligned base and stride keep every
+ * warp store on whole lines, worth ~3 %); d_counts[K] overwritten (may be NULL). */
 int sss_shared_scan(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, const uint32_t* d_lo,
                     const uint32_t* d_hi, int K, void* d_bitvecs, uint64_t stride_bytes,
                     uint64_t* d_counts, void* stream);

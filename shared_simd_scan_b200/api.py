@@ -169,7 +169,7 @@ def shared_scan(packed: torch.Tensor, n: int, w: int, lo, hi=None, out: Optional
     _check_packed(packed, n, w)
     lo32, hi32, K = _bounds(lo, lo if hi is None else hi, packed.device)
     if out is None:
-        stride = (bitvec_bytes(n) + 15) // 16 * 16
+        stride = (bitvec_bytes(n) + 127) // 128 * 128  # whole 128-byte lines per warp store (+3 % at K = 64)
         out = torch.empty((K, stride), dtype=torch.uint8, device=packed.device)
     if out.dim() != 2 or out.shape[0] != K or not out.is_contiguous():
         raise ValueError("out must be a contiguous [K, stride] uint8 tensor")

@@ -78,7 +78,7 @@ def main():
             cnt = torch.empty(K, dtype=torch.int64, device="cuda")
             for op in ops:
                 if op == "shared":
-                    stride = (api.bitvec_bytes(n2) + 15) // 16 * 16
+                    stride = (api.bitvec_bytes(n2) + 127) // 128 * 128
                     out = arena[: K * stride].view(K, stride)
                     f = lambda: api.shared_scan(packed, n2, w, lo_d, hi_d, out=out, counts=cnt)  # noqa: E731
                 else:
