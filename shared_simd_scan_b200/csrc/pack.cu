@@ -17,6 +17,7 @@
 // 2^30..2^34-code columns of BASELINE.json never exist unpacked.
 //
 // Roofline: HBM.  Algorithmic bytes per code = 4 + W/8.
+#include <algorithm>
 #include <array>
 #include <utility>
 
@@ -91,7 +92,18 @@ struct PackBlock<W, 32> {
     static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[W]) {}
 };
 
-constexpr int kPackWarps = 4;  // 128-thread CTAs: 4 warps x (codes 4608 B + words <= 4224 B) of shared memory
+#ifndef SSS_PACK_WARPS
+#define SSS_PACK_WARPS 4
+#endif
+// Measured (tools/ab_pack.py): one short-lived CTA per 4 warp-rounds beats a grid capped at 12 CTAs per SM
+// by 10-30 %, and plain read-only loads beat evict-first streaming loads by 5-8 %.
+#ifndef SSS_PACK_CTAS_PER_SM
+#define SSS_PACK_CTAS_PER_SM (1u << 20)
+#endif
+#ifndef SSS_PACK_LOAD
+#define SSS_PACK_LOAD __ldg
+#endif
+constexpr int kPackWarps = SSS_PACK_WARPS;  // 128-thread CTAs: 4 warps x (codes 4608 B + words <= 4224 B) of shared memory
 
 template <int W>
 __global__ void __launch_bounds__(kPackWarps * 32)
@@ -111,7 +123,7 @@ pack_block_kernel(const uint32_t* __restrict__ codes, uint64_t n_full_blocks, ui
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const uint32_t c = i * 32 + lane;
-            if (c < nb * 8) s_codes[warp][(c >> 3) * 9 + (c & 7)] = __ldcs(src + c);
+            if (c < nb * 8) s_codes[warp][(c >> 3) * 9 + (c & 7)] = SSS_PACK_LOAD(src + c);
         }
         __syncwarp();
         uint32_t out[W];
@@ -147,7 +159,7 @@ static cudaError_t launch_block_w(const Device& dev, const uint32_t* codes, uint
 {
     const uint64_t groups = (n_full_blocks + 31) / 32;
     const uint64_t want = (groups + kPackWarps - 1) / kPackWarps;
-    const uint64_t cap = (uint64_t)dev.sm_count * 12;
+    const uint64_t cap = std::min<uint64_t>((uint64_t)dev.sm_count * SSS_PACK_CTAS_PER_SM, 0x7FFFFFFFull);
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     pack_block_kernel<W><<<grid, kPackWarps * 32, 0, stream>>>(codes, n_full_blocks, packed);
     return cudaGetLastError();
