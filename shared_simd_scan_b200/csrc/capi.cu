@@ -365,7 +365,7 @@ static int shared_scan_body(sss_ctx* ctx, bool linear, const void* d_packed, uin
                             uint64_t stride_bytes, unsigned long long* d_counts, cudaStream_t st)
 {
     if (n == 0) return SSS_OK;
-    if (K <= kNarrowMaxK && w <= kNarrowMaxW)  // few predicates over narrow codes: group-table kernel
+    if (K <= kNarrowMaxK && w <= kFewPredicatesMaxW)  // few predicates: group-table / mask-bucket kernels
         return cuda_status(launch_shared_scan_narrow(ctx->dev, d_packed, n, w, ctx->d_index, K, d_out, stride_bytes / 4,
                                                      linear, d_counts, st));
     if (linear)
@@ -382,9 +382,18 @@ static int shared_impl(sss_ctx* ctx, bool linear, const void* d_packed, uint64_t
     if (K == 1 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0)  // (the scan kernel stores 128-bit pieces)
         return single_predicate_body(ctx, d_packed, n, w, d_lo, d_hi, d_out, d_counts, false, st);
     if (d_counts) SSS_CK(cudaMemsetAsync(d_counts, 0, (size_t)K * sizeof(unsigned long long), st));
-    SSS_CK(launch_build_pred_index(d_lo, d_hi, K, w, ctx->d_index, st));
-    SSS_TRY(shared_scan_body(ctx, linear, d_packed, n, w, K, d_out, stride_bytes, d_counts, st));
-    if (d_counts && !counts_directly(linear, K)) SSS_CK(launch_counts_from_histogram(ctx->d_index, K, d_counts, st));
+    // bitvector layout: predicates in groups whose row table fits in shared memory (shared.cu); the
+    // index buffer is reused group after group in stream order
+    const int G = linear ? K : shared_scan_predicate_group(w, K);
+    for (int k0 = 0; k0 < K; k0 += G) {
+        const int Kg = std::min(G, K - k0);
+        void* out_g = linear ? d_out : static_cast<void*>(static_cast<uint8_t*>(d_out) + (uint64_t)k0 * stride_bytes);
+        unsigned long long* counts_g = d_counts ? d_counts + k0 : nullptr;
+        SSS_CK(launch_build_pred_index(d_lo + k0, d_hi + k0, Kg, w, ctx->d_index, st));
+        SSS_TRY(shared_scan_body(ctx, linear, d_packed, n, w, Kg, out_g, stride_bytes, counts_g, st));
+        if (counts_g && !counts_directly(linear, Kg))
+            SSS_CK(launch_counts_from_histogram(ctx->d_index, Kg, counts_g, st));
+    }
     return SSS_OK;
 }
 

@@ -51,11 +51,17 @@ cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n
                                uint32_t* bitvecs, uint64_t stride_words, unsigned long long* counts, bool count_matches,
                                cudaStream_t stream);
 
+// Bitvector layout, device-resident entry point: the largest number of predicates to hand to one
+// launch_shared_scan call so that the kernel's row table stays in shared memory (K itself when it
+// fits or nothing smaller would); the caller loops over the groups.
+int shared_scan_predicate_group(int w, int K);
+
 // narrow.cu -- K <= kNarrowMaxK predicates over codes of at most kNarrowMaxW bits, either output layout:
 // a table indexed by a GROUP of adjacent codes replaces the per-code interval lookup.  Adds the match
 // counts to counts[0..K) itself (may be null).
 constexpr int kNarrowMaxK = 8;
 constexpr int kNarrowMaxW = 13;  // == the direct-locator widths (predindex.cuh kDirectMaxW)
+constexpr int kFewPredicatesMaxW = 28;  // ... and up to here through the mask-carrying bucket table (narrow.cu)
 cudaError_t launch_shared_scan_narrow(const Device& dev, const void* packed, uint64_t n, int w, const void* index,
                                       int K, void* out, uint64_t stride_words, bool linear,
                                       unsigned long long* counts, cudaStream_t stream);

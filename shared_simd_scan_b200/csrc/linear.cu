@@ -41,7 +41,11 @@ struct LinearCfg {
 };
 
 // more than this many predicates: one warp per block (shared_scan_linear_wide_kernel)
-constexpr int kLinearWideMinK = 16 * 32;
+#ifndef SSS_LINEAR_WIDE_MIN_K
+#define SSS_LINEAR_WIDE_MIN_K (16 * 32)
+#endif
+constexpr int kLinearWideMinK = SSS_LINEAR_WIDE_MIN_K;
+constexpr int kLinearWideFallbackK = 12 * 32;  // ... and from here on when the merged row table does not fit
 
 // in : a[8i + e] byte p bit f  = predicate 8p+f on code 8i+e           (i = row, e = code in group)
 // out: a[8i + 4*f2 + p] byte (f & 3) bit e, f2 = f >> 2                 = row i, bytes 8p+4*f2 .. +3
@@ -364,7 +368,7 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
 
 template <int W, bool kSmem>
 static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, const void* index, int K, uint8_t* out,
-                             unsigned long long* counts, bool count_matches, const IndexSmemPlan& plan,
+                             unsigned long long* counts, bool count_matches, const IndexSmemPlan& plan, bool wide,
                              cudaStream_t stream)
 {
     using Cfg = LinearCfg<W>;
@@ -374,7 +378,7 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    if (K > kLinearWideMinK) {
+    if (wide) {
         static size_t configured_wide[64] = {};
         if (configured_wide[dev.ordinal & 63] < smem) {
             cudaError_t e = cudaFuncSetAttribute(shared_scan_linear_wide_kernel<W, kSmem>,
@@ -402,13 +406,19 @@ template <int W>
 static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K, uint8_t* out,
                             unsigned long long* counts, bool count_matches, cudaStream_t stream)
 {
-    // the wide kernel reads mask rows lane-contiguously (conflict-free already): no mask replicas
-    const bool wide = K > kLinearWideMinK;
-    const IndexSmemPlan plan = plan_index_smem(K, W, LinearCfg<W>::kRingBytes, /*use_hist=*/K > kDirectCountMaxK,
-                                               /*merged_ok=*/!wide);
+    // the wide kernel reads mask rows lane-contiguously (conflict-free already): no mask replicas.  It
+    // also takes over from kLinearWideFallbackK predicates on when the thread-per-block kernel's merged
+    // row table does not fit (K = 512 at W >= 30: 0.46 against 0.21 of the HBM peak).
+    bool wide = K > kLinearWideMinK;
+    IndexSmemPlan plan = plan_index_smem(K, W, LinearCfg<W>::kRingBytes, /*use_hist=*/K > kDirectCountMaxK,
+                                         /*merged_ok=*/!wide);
+    if (!wide && !plan.merged && K >= kLinearWideFallbackK) {
+        wide = true;
+        plan = plan_index_smem(K, W, LinearCfg<W>::kRingBytes, /*use_hist=*/true, /*merged_ok=*/false);
+    }
     if (plan.masks_in_smem)
-        return launch_ws<W, true>(dev, packed, n, index, K, out, counts, count_matches, plan, stream);
-    return launch_ws<W, false>(dev, packed, n, index, K, out, counts, count_matches, plan, stream);
+        return launch_ws<W, true>(dev, packed, n, index, K, out, counts, count_matches, plan, wide, stream);
+    return launch_ws<W, false>(dev, packed, n, index, K, out, counts, count_matches, plan, wide, stream);
 }
 
 using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, uint8_t*,

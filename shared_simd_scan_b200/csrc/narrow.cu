@@ -1,4 +1,6 @@
-// narrow.cu -- shared scans with at most 8 predicates over NARROW codes (W <= 13), both output layouts.
+// narrow.cu -- shared scans with at most 8 predicates, both output layouts: NARROW codes (W <= 13) through
+// a table indexed by groups of codes (below), wider codes (14..28 bit) through a bucket table whose
+// entries carry the match masks (second half of the file).
 //
 // The index-driven kernels (shared.cu, linear.cu) spend ~12 instructions per code at K <= 8: extract
 // the code, look up its interval, look up the interval's mask row.  That is right for wide codes, but
@@ -197,6 +199,200 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
     }
 }
 
+// ---- up to 8 predicates over WIDER codes (14 <= W <= kFewMaxW): the bucket word carries the masks ----
+//
+// From 14 bits on a code is located through the 8192-bucket locator, and the index-driven kernels then
+// read the interval's mask row: two dependent, randomly addressed shared-memory loads and ~18
+// instructions per code (profiles/r01_ncu_v3_shared_w17_k8.txt: shared-memory pipe 79 %, issue 71 %,
+// 0.64 of the HBM peak).  With at most 8 predicates the two mask bytes a bucket can resolve to fit into
+// the bucket word itself:
+//
+//     entry = thr15 << 17 | several << 16 | mask_after << 8 | mask_before
+//
+// thr15 = the top 15 bits of the standard word's 19-bit threshold (predindex.cuh; exact while the
+// code's bits below the bucket bits number at most 15, i.e. W <= 28).  The code is extracted RIGHT-
+// aligned (v: code in the low W bits, later codes above), so `v << (45 - W)` is the threshold field
+// with zeros below it -- `(v << (45 - W)) > entry` is the compare of the standard lookup, and the
+// entry's low bits cannot turn a tie into "greater".  The table address is one rotate + one LOP3
+// (`(rot(v) & index bits) | lane replica`).  Every CTA derives the table in its prologue from the
+// call's standard index.  Codes in a `several` bucket (two or more inner breakpoints: every equality
+// predicate) are patched from the global index by the blocks that met one.
+constexpr int kFewMaxW = kFewPredicatesMaxW;
+constexpr uint32_t kFewSeveral = 1u << 16;
+
+template <int W>
+struct FewCfg {
+    static constexpr int kBlocksPerTile = kNThreads;  // one block per thread per tile
+    static constexpr int kTileBytes = kBlocksPerTile * W * 4;
+    static constexpr int kStages = kTileBytes >= 32 * 1024 ? 2 : 3;
+    using Ring = TileRing<kTileBytes, kStages>;
+    static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
+};
+
+// code J of the block in the LOW W bits (garbage -- the following codes -- above)
+template <int W, int J>
+__device__ __forceinline__ uint32_t low_aligned_code(const uint32_t (&x)[W])
+{
+    constexpr int bit = J * W, wi = bit >> 5, sh = bit & 31;
+    if constexpr (sh == 0) {
+        return x[wi];
+    } else if constexpr (sh + W <= 32) {
+        return x[wi] >> sh;
+    } else {
+        return __funnelshift_r(x[wi], x[wi + 1 < W ? wi + 1 : wi], sh);
+    }
+}
+
+struct FewTable {
+    uint32_t base;      // shared-window address of the table (warp-uniform)
+    uint32_t lane_off;  // byte offset of this lane's replica inside an entry group
+    uint32_t idx_mask;  // 0x1FFF << (2 + rep_log2)
+    uint32_t rot;       // rotate-right distance that moves the code's top 13 bits onto idx_mask
+};
+
+template <int W, int J>
+struct FewLookups {
+    static __device__ __forceinline__ void run(const uint32_t (&x)[W], const FewTable& tb, uint32_t (&m)[32],
+                                               uint32_t& flags)
+    {
+        const uint32_t v = low_aligned_code<W, J>(x);
+        const uint32_t off = bit_select(__funnelshift_r(v, v, tb.rot), tb.lane_off, tb.idx_mask);
+        uint32_t e;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(off + tb.base));
+        flags |= e;
+        m[J] = (v << (45 - W)) > e ? e >> 8 : e;  // byte 0 = the code's match mask
+        FewLookups<W, J + 1>::run(x, tb, m, flags);
+    }
+    static __device__ __forceinline__ void fix(const uint32_t (&x)[W], const uint8_t* __restrict__ g_index,
+                                               uint32_t row_words, uint32_t (&m)[32])
+    {
+        const uint32_t t = low_aligned_code<W, J>(x) << (32 - W);  // left-aligned, zeros below
+        const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kLocator) +
+                                 (t >> (32 - kBucketBits)));
+        if (e & kSeveralBit) {
+            const uint32_t* thr = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kThr);
+            uint32_t i = e & kBucketIdMask;
+            while (t > __ldg(thr + i)) i++;  // thr[num_bp] = 0xFFFFFFFF ends the walk
+            m[J] = __ldg(reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kMasks) + i * row_words);
+        }
+        FewLookups<W, J + 1>::fix(x, g_index, row_words, m);
+    }
+};
+template <int W>
+struct FewLookups<W, 32> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[W], const FewTable&, uint32_t (&)[32], uint32_t&) {}
+    static __device__ __forceinline__ void fix(const uint32_t (&)[W], const uint8_t*, uint32_t, uint32_t (&)[32]) {}
+};
+
+template <int W>
+__global__ void __launch_bounds__(kNThreads, 1)
+shared_scan_few_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
+                       const uint8_t* __restrict__ g_index, int K, void* __restrict__ out, uint64_t stride_words,
+                       bool linear, unsigned long long* __restrict__ counts, int rep_log2)
+{
+    using Cfg = FewCfg<W>;
+    static_assert(W > kDirectMaxW && W <= kFewMaxW && W - kBucketBits <= 15, "bucket locator widths, 15-bit thresholds");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(g_index + PredIndexLayout::kHeader);
+    const uint32_t row_words = h->row_words;
+    // ---- prologue: the mask-carrying bucket table, `R` replicas interleaved entry by entry ------------
+    {
+        const uint32_t num_bp = h->num_bp;
+        const uint32_t* bucket = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kLocator);
+        const uint32_t* masks = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kMasks);
+        uint32_t* table = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);
+        for (uint32_t i = threadIdx.x; i < ((uint32_t)kBuckets << rep_log2); i += kNThreads) {
+            const uint32_t e = bucket[i >> rep_log2];
+            const uint32_t id = e & kBucketIdMask;
+            const uint32_t before = masks[id * row_words] & 0xFFu;
+            const uint32_t after = id < num_bp ? masks[(id + 1) * row_words] & 0xFFu : 0u;
+            table[i] = (e & 0xFFFE0000u) | ((e & kSeveralBit) ? kFewSeveral : 0u) | (after << 8) | before;
+        }
+    }
+    const uint32_t R = 1u << rep_log2;
+    FewTable tb;
+    tb.base = smem_u32(smem + Cfg::kRingBytes);
+    tb.lane_off = (threadIdx.x & (R - 1)) << 2;
+    tb.idx_mask = (uint32_t)(kBuckets - 1) << (2 + rep_log2);
+    tb.rot = (uint32_t)(W - kBucketBits - 2 - rep_log2) & 31u;
+    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    ring.start();  // contains the __syncthreads that publishes the table
+
+    using Rot = BlockRot<W, 1>;
+    const uint32_t lane_rot = Rot::lane_rot();
+    const uint64_t n_blocks = (n + 31) >> 5;
+    const uint32_t tail_bits = (uint32_t)(n & 31);
+    uint32_t direct[kNarrowMaxK] = {};
+
+    uint32_t iter = 0;
+    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
+        ring.wait(iter);
+        const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
+        uint32_t x[W];
+        load_block<W, 1>(buf, threadIdx.x, x, lane_rot);  // (W = 16, 24: rotated by lane_rot pieces, see BlockRot)
+        uint32_t loaded = 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) loaded |= x[k];
+        ring.release_warp(iter, tile, loaded);
+        const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
+        if (gb >= n_blocks) continue;
+        const uint32_t keep = (tail_bits != 0 && gb == n_blocks - 1) ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
+
+        uint32_t m[32], flags = 0;
+        FewLookups<W, 0>::run(x, tb, m, flags);
+        if (flags & kFewSeveral) FewLookups<W, 0>::fix(x, g_index, row_words, m);
+        uint32_t r[8];
+        transpose32x8(m, r);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if constexpr (Rot::kRot) r[k] = __funnelshift_l(r[k], r[k], lane_rot * Rot::kPieceCodes);
+            r[k] &= keep;
+            if (k < K) direct[k] += __popc(r[k]);
+        }
+        if (linear) {
+            store_block_small(static_cast<uint8_t*>(out) + gb * 4 * (uint64_t)K, r, K);
+        } else {
+            uint32_t* p = static_cast<uint32_t*>(out) + gb;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (k < K) st_stream_u32(p, r[k]);
+                p += stride_words;
+            }
+        }
+    }
+    if (counts != nullptr) {
+#pragma unroll
+        for (int k = 0; k < kNarrowMaxK; k++) {
+            const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, direct[k]);
+            if ((threadIdx.x & 31) == 0 && k < K && s != 0) atomicAdd(&counts[k], (unsigned long long)s);
+        }
+    }
+}
+
+template <int W>
+static cudaError_t launch_few_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K, void* out,
+                                uint64_t stride_words, bool linear, unsigned long long* counts, cudaStream_t stream)
+{
+    using Cfg = FewCfg<W>;
+    const int r = narrow_rep_log2(Cfg::kRingBytes, kBuckets);
+    const size_t smem = Cfg::kRingBytes + ((size_t)kBuckets * 4 << r) + 64;
+    static size_t configured[64] = {};
+    if (configured[dev.ordinal & 63] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(shared_scan_few_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev.ordinal & 63] = smem;
+    }
+    const uint64_t n_blocks = (n + 31) / 32;
+    const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
+    const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
+    const uint64_t max_ctas = (uint64_t)dev.sm_count;
+    const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
+    shared_scan_few_kernel<W><<<grid, kNThreads, smem, stream>>>(packed, readable, n, static_cast<const uint8_t*>(index),
+                                                                  K, out, stride_words, linear, counts, r);
+    return cudaGetLastError();
+}
+
 template <int W>
 static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, const void* index, int K, void* out,
                             uint64_t stride_words, bool linear, unsigned long long* counts, cudaStream_t stream)
@@ -230,12 +426,20 @@ static constexpr auto make_table(std::integer_sequence<int, Ws...>)
 {
     return std::array<Launcher, sizeof...(Ws)>{&launch_w<Ws + 1>...};
 }
+template <int... Ws>
+static constexpr auto make_few_table(std::integer_sequence<int, Ws...>)
+{
+    return std::array<Launcher, sizeof...(Ws)>{&launch_few_w<Ws + kNarrowMaxW + 1>...};
+}
 
 cudaError_t launch_shared_scan_narrow(const Device& dev, const void* packed, uint64_t n, int w, const void* index,
                                       int K, void* out, uint64_t stride_words, bool linear,
                                       unsigned long long* counts, cudaStream_t stream)
 {
     static constexpr auto table = make_table(std::make_integer_sequence<int, kNarrowMaxW>{});
+    static constexpr auto few = make_few_table(std::make_integer_sequence<int, kFewMaxW - kNarrowMaxW>{});
+    if (w > kNarrowMaxW)
+        return few[w - kNarrowMaxW - 1](dev, packed, n, index, K, out, stride_words, linear, counts, stream);
     return table[w - 1](dev, packed, n, index, K, out, stride_words, linear, counts, stream);
 }
 

@@ -393,6 +393,39 @@ static constexpr auto make_table(std::integer_sequence<int, Ws...>)
     return std::array<Launcher, sizeof...(Ws)>{&launch_w<Ws + 1>...};
 }
 
+// Predicate groups.  Once the merged row table of all K predicates no longer fits in shared memory
+// the kernels above fall to 0.31-0.36 of the HBM peak (rows read through L1, or the warp-per-block
+// kernel's 64-byte runs), while a table that fits runs at 0.60 whatever the width.  The bitvectors of
+// different predicates are independent, so the device-resident entry point evaluates such a K as
+// ceil(K / G) scans of G predicates each (own index, own bitvector slice, own counts): the column is
+// read ceil(K / G) times, which at K / 8 output bytes per code is noise (K = 1024, 32 bit, G = 256:
+// 16 B read against 128 B written per code).  Returns G (a multiple of 32), or K when the table fits
+// or no smaller group would fit either.
+template <int W>
+static int group_w(int K)
+{
+    auto merged = [](int k) {
+        return plan_index_smem(k, W, SharedCfg<W>::kRingBytes, /*use_hist=*/k > kDirectCountMaxK, /*merged_ok=*/true)
+                   .merged != 0;
+    };
+    if (K <= 128 || merged(K)) return K;
+    for (int g = 512; g >= 128; g >>= 1)
+        if (g < K && merged(g)) return g;
+    return K;
+}
+
+template <int... Ws>
+static constexpr auto make_group_table(std::integer_sequence<int, Ws...>)
+{
+    return std::array<int (*)(int), sizeof...(Ws)>{&group_w<Ws + 1>...};
+}
+
+int shared_scan_predicate_group(int w, int K)
+{
+    static constexpr auto table = make_group_table(std::make_integer_sequence<int, 32>{});
+    return table[w - 1](K);
+}
+
 cudaError_t launch_shared_scan(const Device& dev, const void* packed, uint64_t n, int w, const void* index, int K,
                                uint32_t* bitvecs, uint64_t stride_words, unsigned long long* counts, bool count_matches,
                                cudaStream_t stream)

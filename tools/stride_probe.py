@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Developer probe: does the caller-chosen bitvector stride of sss_shared_scan matter?  (K = 64, 17 bit)"""
+"""Developer probe: does the caller-chosen bitvector stride of sss_shared_scan matter?
+
+    python tools/stride_probe.py [w=17] [K=64]"""
 import os
 import sys
 
@@ -8,7 +10,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from shared_simd_scan_b200 import api  # noqa: E402
 
-w, K, n = int(sys.argv[1]) if len(sys.argv) > 1 else 17, 64, 1 << 30
+w = int(sys.argv[1]) if len(sys.argv) > 1 else 17
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+n = (1 << 30) if K <= 64 else (1 << 36) // K // 8
 m = (1 << w) - 1
 packed = api.generate_packed(n, w, seed=42 + w)
 g = torch.Generator().manual_seed(42 + K)
