@@ -227,46 +227,90 @@ struct FewCfg {
     static constexpr int kStages = kTileBytes >= 32 * 1024 ? 2 : 3;
     using Ring = TileRing<kTileBytes, kStages>;
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
+    // lane-private replicas of the table from what the ring leaves over (compile-time: the index shift
+    // below then folds into the code's extraction shift)
+    static constexpr int rep_log2()
+    {
+        int r = 5;
+        while (r > 0 && kRingBytes + ((kBuckets * 4) << r) + 64 > 220 * 1024) r--;
+        return r;
+    }
+    static constexpr int kRepLog2 = rep_log2();
+    static constexpr int kTableBytes = (kBuckets * 4) << kRepLog2;
+    static constexpr uint32_t kIdxMask = (uint32_t)(kBuckets - 1) << (2 + kRepLog2);
+    // right shift that moves a RIGHT-aligned code's top 13 bits onto kIdxMask (negative: left shift)
+    static constexpr int kIdxShift = W - kBucketBits - 2 - kRepLog2;
 };
 
-// code J of the block in the LOW W bits (garbage -- the following codes -- above)
-template <int W, int J>
-__device__ __forceinline__ uint32_t low_aligned_code(const uint32_t (&x)[W])
+// x >> S for S >= 0, x << -S otherwise
+template <int S>
+__device__ __forceinline__ uint32_t shift_right_signed(uint32_t x)
 {
+    if constexpr (S >= 0) return x >> S;
+    else return x << (-S);
+}
+
+// Pipe balance.  Integer work issues on two pipes, each good for one warp instruction every two
+// cycles per scheduler: shifts, LOP3, PRMT and compares on the ALU pipe, IMAD on the FMA pipe.  A
+// lookup written with shifts alone is bound by the ALU pipe (ncu, 17 bit: ALU 86 %, FMA 8 %), so half
+// of the shifts are issued as multiplies: `x << s` is IMAD.SHL anyway, and `x >> s` = umulhi(x, 2^(32-s))
+// becomes IMAD.HI when the power of two comes from a kernel parameter (an immediate would be folded
+// back into a shift by ptxas).
+struct Pow2Table {
+    uint32_t p[32];  // p[k] = 1 << k
+};
+
+template <int S>
+__device__ __forceinline__ uint32_t shr_fma(uint32_t x, const Pow2Table& P)
+{
+    if constexpr (S == 0) return x;
+    else return __umulhi(x, P.p[32 - S]);
+}
+
+// Code J of the block: shared-memory address of its table entry and the threshold field
+// `v << (45 - W)` (v = the right-aligned code, later codes above it).
+template <int W, int J>
+__device__ __forceinline__ void few_code(const uint32_t (&x)[W], const Pow2Table& P, uint32_t table_base,
+                                         uint32_t lane_off, uint32_t& addr, uint32_t& field)
+{
+    using Cfg = FewCfg<W>;
     constexpr int bit = J * W, wi = bit >> 5, sh = bit & 31;
-    if constexpr (sh == 0) {
-        return x[wi];
-    } else if constexpr (sh + W <= 32) {
-        return x[wi] >> sh;
+    constexpr bool kFmaRoute = (J % 3) != 0;  // address arithmetic on the FMA pipe for two codes out of three
+    uint32_t v;
+    if constexpr (sh + W <= 32) v = kFmaRoute ? x[wi] >> sh : shr_fma<sh>(x[wi], P);
+    else v = __funnelshift_r(x[wi], x[wi + 1 < W ? wi + 1 : wi], sh);
+    field = v << (45 - W);
+    if constexpr (kFmaRoute) {
+        const uint32_t idx = __umulhi(v << (32 - W), P.p[kBucketBits]);  // top 13 bits of the code
+        addr = idx * (4u << Cfg::kRepLog2) + (table_base + lane_off);
     } else {
-        return __funnelshift_r(x[wi], x[wi + 1 < W ? wi + 1 : wi], sh);
+        addr = bit_select(shift_right_signed<Cfg::kIdxShift>(v), lane_off, Cfg::kIdxMask) + table_base;
     }
 }
 
-struct FewTable {
-    uint32_t base;      // shared-window address of the table (warp-uniform)
-    uint32_t lane_off;  // byte offset of this lane's replica inside an entry group
-    uint32_t idx_mask;  // 0x1FFF << (2 + rep_log2)
-    uint32_t rot;       // rotate-right distance that moves the code's top 13 bits onto idx_mask
-};
-
 template <int W, int J>
 struct FewLookups {
-    static __device__ __forceinline__ void run(const uint32_t (&x)[W], const FewTable& tb, uint32_t (&m)[32],
-                                               uint32_t& flags)
+    // two codes per step: their entries join the block's `several` flags in ONE three-input LOP3
+    static __device__ __forceinline__ void run(const uint32_t (&x)[W], const Pow2Table& P, uint32_t table_base,
+                                               uint32_t lane_off, uint32_t (&m)[32], uint32_t& flags)
     {
-        const uint32_t v = low_aligned_code<W, J>(x);
-        const uint32_t off = bit_select(__funnelshift_r(v, v, tb.rot), tb.lane_off, tb.idx_mask);
-        uint32_t e;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(off + tb.base));
-        flags |= e;
-        m[J] = (v << (45 - W)) > e ? e >> 8 : e;  // byte 0 = the code's match mask
-        FewLookups<W, J + 1>::run(x, tb, m, flags);
+        uint32_t addr0, field0, addr1, field1, e0, e1;
+        few_code<W, J>(x, P, table_base, lane_off, addr0, field0);
+        few_code<W, J + 1>(x, P, table_base, lane_off, addr1, field1);
+        asm("ld.shared.u32 %0, [%1];" : "=r"(e0) : "r"(addr0));
+        asm("ld.shared.u32 %0, [%1];" : "=r"(e1) : "r"(addr1));
+        asm("lop3.b32 %0, %0, %1, %2, 0xFE;" : "+r"(flags) : "r"(e0), "r"(e1));
+        m[J] = field0 > e0 ? __umulhi(e0, P.p[24]) : e0;  // (e >> 8 as IMAD.HI); byte 0 = the code's match mask
+        m[J + 1] = field1 > e1 ? __umulhi(e1, P.p[24]) : e1;
+        FewLookups<W, J + 2>::run(x, P, table_base, lane_off, m, flags);
     }
     static __device__ __forceinline__ void fix(const uint32_t (&x)[W], const uint8_t* __restrict__ g_index,
                                                uint32_t row_words, uint32_t (&m)[32])
     {
-        const uint32_t t = low_aligned_code<W, J>(x) << (32 - W);  // left-aligned, zeros below
+        constexpr int bit = J * W, wi = bit >> 5, sh = bit & 31;
+        uint32_t v = x[wi] >> sh;
+        if constexpr (sh + W > 32) v = __funnelshift_r(x[wi], x[wi + 1 < W ? wi + 1 : wi], sh);
+        const uint32_t t = v << (32 - W);  // left-aligned, zeros below
         const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kLocator) +
                                  (t >> (32 - kBucketBits)));
         if (e & kSeveralBit) {
@@ -280,17 +324,23 @@ struct FewLookups {
 };
 template <int W>
 struct FewLookups<W, 32> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[W], const FewTable&, uint32_t (&)[32], uint32_t&) {}
+    static __device__ __forceinline__ void run(const uint32_t (&)[W], const Pow2Table&, uint32_t, uint32_t,
+                                               uint32_t (&)[32], uint32_t&)
+    {
+    }
     static __device__ __forceinline__ void fix(const uint32_t (&)[W], const uint8_t*, uint32_t, uint32_t (&)[32]) {}
 };
 
-template <int W>
+template <int W, bool kAll8>
 __global__ void __launch_bounds__(kNThreads, 1)
 shared_scan_few_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
-                       const uint8_t* __restrict__ g_index, int K, void* __restrict__ out, uint64_t stride_words,
-                       bool linear, unsigned long long* __restrict__ counts, int rep_log2)
+                       const uint8_t* __restrict__ g_index, int K_arg, void* __restrict__ out, uint64_t stride_words,
+                       bool linear, unsigned long long* __restrict__ counts, const Pow2Table P)
 {
+    // kAll8: exactly 8 predicates (no per-predicate guards in the epilogue)
+    const int K = kAll8 ? 8 : K_arg;
     using Cfg = FewCfg<W>;
+    constexpr int rep_log2 = Cfg::kRepLog2;
     static_assert(W > kDirectMaxW && W <= kFewMaxW && W - kBucketBits <= 15, "bucket locator widths, 15-bit thresholds");
     extern __shared__ __align__(128) uint8_t smem[];
     const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(g_index + PredIndexLayout::kHeader);
@@ -309,12 +359,8 @@ shared_scan_few_kernel(const void* __restrict__ packed, uint64_t readable_bytes1
             table[i] = (e & 0xFFFE0000u) | ((e & kSeveralBit) ? kFewSeveral : 0u) | (after << 8) | before;
         }
     }
-    const uint32_t R = 1u << rep_log2;
-    FewTable tb;
-    tb.base = smem_u32(smem + Cfg::kRingBytes);
-    tb.lane_off = (threadIdx.x & (R - 1)) << 2;
-    tb.idx_mask = (uint32_t)(kBuckets - 1) << (2 + rep_log2);
-    tb.rot = (uint32_t)(W - kBucketBits - 2 - rep_log2) & 31u;
+    const uint32_t table_base = smem_u32(smem + Cfg::kRingBytes);
+    const uint32_t lane_off = (threadIdx.x & ((1u << rep_log2) - 1u)) << 2;
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();  // contains the __syncthreads that publishes the table
 
@@ -339,23 +385,28 @@ shared_scan_few_kernel(const void* __restrict__ packed, uint64_t readable_bytes1
         const uint32_t keep = (tail_bits != 0 && gb == n_blocks - 1) ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
 
         uint32_t m[32], flags = 0;
-        FewLookups<W, 0>::run(x, tb, m, flags);
+        FewLookups<W, 0>::run(x, P, table_base, lane_off, m, flags);
         if (flags & kFewSeveral) FewLookups<W, 0>::fix(x, g_index, row_words, m);
         uint32_t r[8];
         transpose32x8(m, r);
+        if constexpr (Rot::kRot) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if constexpr (Rot::kRot) r[k] = __funnelshift_l(r[k], r[k], lane_rot * Rot::kPieceCodes);
-            r[k] &= keep;
-            if (k < K) direct[k] += __popc(r[k]);
+            for (int k = 0; k < 8; k++) r[k] = __funnelshift_l(r[k], r[k], lane_rot * Rot::kPieceCodes);
         }
+        if (keep != 0xFFFFFFFFu) {  // the column's ragged last block only
+#pragma unroll
+            for (int k = 0; k < 8; k++) r[k] &= keep;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (kAll8 || k < K) direct[k] += __popc(r[k]);
         if (linear) {
             store_block_small(static_cast<uint8_t*>(out) + gb * 4 * (uint64_t)K, r, K);
         } else {
             uint32_t* p = static_cast<uint32_t*>(out) + gb;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                if (k < K) st_stream_u32(p, r[k]);
+                if (kAll8 || k < K) st_stream_u32(p, r[k]);
                 p += stride_words;
             }
         }
@@ -374,12 +425,16 @@ static cudaError_t launch_few_w(const Device& dev, const void* packed, uint64_t 
                                 uint64_t stride_words, bool linear, unsigned long long* counts, cudaStream_t stream)
 {
     using Cfg = FewCfg<W>;
-    const int r = narrow_rep_log2(Cfg::kRingBytes, kBuckets);
-    const size_t smem = Cfg::kRingBytes + ((size_t)kBuckets * 4 << r) + 64;
+    const size_t smem = Cfg::kRingBytes + Cfg::kTableBytes + 64;
+    Pow2Table P;
+    for (int k = 0; k < 32; k++) P.p[k] = 1u << k;
     static size_t configured[64] = {};
     if (configured[dev.ordinal & 63] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(shared_scan_few_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(shared_scan_few_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(shared_scan_few_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev.ordinal & 63] = smem;
     }
@@ -388,8 +443,12 @@ static cudaError_t launch_few_w(const Device& dev, const void* packed, uint64_t 
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_few_kernel<W><<<grid, kNThreads, smem, stream>>>(packed, readable, n, static_cast<const uint8_t*>(index),
-                                                                  K, out, stride_words, linear, counts, r);
+    if (K == 8)
+        shared_scan_few_kernel<W, true><<<grid, kNThreads, smem, stream>>>(
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, P);
+    else
+        shared_scan_few_kernel<W, false><<<grid, kNThreads, smem, stream>>>(
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, P);
     return cudaGetLastError();
 }
 
