@@ -89,12 +89,14 @@ struct GroupLookups<W, NarrowCfg<W>::kLookups> {
     }
 };
 
-template <int W>
+template <int W, bool kAll8>
 __global__ void __launch_bounds__(kNThreads, kNCtasPerSm)
 shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
-                          const uint8_t* __restrict__ g_index, int K, void* __restrict__ out, uint64_t stride_words,
+                          const uint8_t* __restrict__ g_index, int K_arg, void* __restrict__ out, uint64_t stride_words,
                           bool linear, unsigned long long* __restrict__ counts, int rep_log2)
 {
+    // kAll8: exactly 8 predicates (no per-predicate guards in the epilogue)
+    const int K = kAll8 ? 8 : K_arg;
     using Cfg = NarrowCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
     // ---- prologue: the group table, `R` replicas interleaved entry by entry --------------------------
@@ -172,19 +174,24 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
                 }
             }
             if constexpr (Cfg::kG != 1) transpose_bits_32x8(r);
+            if constexpr (Rot::kRot) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if constexpr (Rot::kRot) r[k] = __funnelshift_l(r[k], r[k], lane_rot * Rot::kPieceCodes);
-                r[k] &= keep;
-                if (k < K) direct[k] += __popc(r[k]);
+                for (int k = 0; k < 8; k++) r[k] = __funnelshift_l(r[k], r[k], lane_rot * Rot::kPieceCodes);
             }
+            if (keep != 0xFFFFFFFFu) {  // the column's ragged last block only
+#pragma unroll
+                for (int k = 0; k < 8; k++) r[k] &= keep;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (kAll8 || k < K) direct[k] += __popc(r[k]);
             if (linear) {
                 store_block_small(static_cast<uint8_t*>(out) + gb * 4 * (uint64_t)K, r, K);
             } else {
                 uint32_t* p = static_cast<uint32_t*>(out) + gb;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    if (k < K) st_stream_u32(p, r[k]);
+                    if (kAll8 || k < K) st_stream_u32(p, r[k]);
                     p += stride_words;
                 }
             }
@@ -461,8 +468,11 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, c
     const size_t smem = Cfg::kRingBytes + ((size_t)Cfg::kEntries * 4 << r) + 64;
     static size_t configured[64] = {};
     if (configured[dev.ordinal & 63] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(shared_scan_narrow_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(shared_scan_narrow_kernel<W, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(shared_scan_narrow_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev.ordinal & 63] = smem;
     }
@@ -471,9 +481,12 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, c
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * kNCtasPerSm;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_narrow_kernel<W><<<grid, kNThreads, smem, stream>>>(packed, readable, n,
-                                                                     static_cast<const uint8_t*>(index), K, out,
-                                                                     stride_words, linear, counts, r);
+    if (K == 8)
+        shared_scan_narrow_kernel<W, true><<<grid, kNThreads, smem, stream>>>(
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, r);
+    else
+        shared_scan_narrow_kernel<W, false><<<grid, kNThreads, smem, stream>>>(
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, r);
     return cudaGetLastError();
 }
 
