@@ -516,6 +516,19 @@ __device__ __forceinline__ uint32_t bit_select(uint32_t a, uint32_t b, uint32_t 
     return d;
 }
 
+// Pipe balance (measured, not adopted here).  Integer instructions issue on two pipes: LOP3, PRMT,
+// shifts and compares on the ALU pipe, IMAD on the FMA pipe.  An exchange stage is 3 ALU + 1 FMA
+// instructions per register pair (ptxas already turns `b << S` into IMAD.SHL).  Issuing `a >> S` as
+// umulhi(a, 2^(32-S)) = IMAD.HI (the power of two loaded from constant memory so that ptxas cannot fold
+// it back into a shift) makes it 2 + 2 -- and was SLOWER in every kernel that transposes (linear K = 64:
+// 0.85 -> 0.80 of the HBM peak, linear K = 1024: 0.66 -> 0.62, shared K = 64 unchanged): IMAD.HI does not
+// run at the rate of a shift.  The K <= 8 lookup in narrow.cu, which was at 86 % ALU pipe utilisation,
+// is the one place where the trade pays.  -DSSS_SHR_FMA=1 rebuilds the variant.
+#ifndef SSS_SHR_FMA
+#define SSS_SHR_FMA 0
+#endif
+static __constant__ uint32_t c_shr_mul[5] = {0u, 1u << 31, 1u << 30, 0u, 1u << 28};  // [S] = 2^(32 - S), S = 1, 2, 4
+
 // one exchange stage on a register pair: swaps the high S-bit groups of `lo` with the low ones of `hi`
 template <int S>
 __device__ __forceinline__ void exchange_bits(uint32_t& lo, uint32_t& hi)
@@ -523,7 +536,11 @@ __device__ __forceinline__ void exchange_bits(uint32_t& lo, uint32_t& hi)
     constexpr uint32_t M = S == 4 ? 0x0F0F0F0Fu : (S == 2 ? 0x33333333u : 0x55555555u);
     const uint32_t a = lo, b = hi;
     lo = bit_select(a, b << S, M);
+#if SSS_SHR_FMA
+    hi = bit_select(__umulhi(a, c_shr_mul[S]), b, M);
+#else
     hi = bit_select(a >> S, b, M);
+#endif
 }
 
 // in : a[j] bit k  = element (j, k)        (j = code index, k = predicate index)
