@@ -288,6 +288,64 @@ def test_shared_scan_clustered_bounds_and_codes(sss, w):
     assert (host(cnt2).astype(np.uint64) == lcnt).all()
 
 
+@pytest.mark.parametrize("w", list(range(12, 31)))
+@pytest.mark.parametrize("K", [1, 5, 8])
+def test_few_predicates_clustered(sss, w, K):
+    """K <= 8 at every width around the mask-carrying bucket table (14..28 bit; 12, 13 and 29, 30 take
+    the neighbouring kernels): codes and bounds crowded into a few buckets so that buckets with
+    several breakpoints, equality predicates, ties on a threshold and the bucket's first / last code
+    all occur; ragged column, both layouts, counts."""
+    n = 50_021
+    rng = np.random.default_rng(1000 * w + K)
+    m = (1 << w) - 1
+    span = 1 << max(w - 13, 1)                          # codes per 13-bit bucket
+    center = (m // 3) // span * span                     # a bucket boundary
+    codes = (center + rng.integers(-3 * span, 3 * span, size=n)).astype(np.int64)
+    codes[::5] = rng.integers(0, m + 1, size=len(codes[::5]))
+    codes[1::11] = center                                # the bucket's first code
+    codes[2::11] = center - 1                            # the previous bucket's last code
+    codes = np.clip(codes, 0, m).astype(np.uint32)
+    packed = B.pack(codes, w)
+    lo = np.clip(center + rng.integers(-2 * span, 2 * span, size=K), 0, m).astype(np.uint64)
+    hi = np.minimum(lo + rng.integers(0, span, size=K).astype(np.uint64), m)
+    lo[0], hi[0] = center, center                        # equality on a bucket boundary
+    if K > 2:
+        lo[1], hi[1] = center - 1, center + span - 1     # ends exactly on a bucket's last code
+        lo[2], hi[2] = 0, m                              # everything
+    if K > 4:
+        lo[3], hi[3] = 7, 3                              # empty
+        lo[4], hi[4] = m, m                              # the top code only
+    exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
+    bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi)
+    nb = (n + 7) // 8
+    assert (host(bv)[:, :nb] == exp).all()
+    assert (host(cnt).astype(np.uint64) == ecnt).all()
+    lexp, lcnt = B.shared_scan_linear(packed, n, w, lo, hi, granule=1)
+    lin, cnt2 = sss.shared_scan_linear(dev(packed), n, w, lo, hi)
+    assert (host(lin)[:nb] == lexp).all()
+    assert (host(cnt2).astype(np.uint64) == lcnt).all()
+
+
+def test_predicate_groups_match_single_scans(sss):
+    """K = 1024 at 23 bit is evaluated in predicate groups (the merged row table of all 1024 does not
+    fit in shared memory): every bitvector and count must equal the oracle's, duplicates and empty
+    predicates across group boundaries included."""
+    w, K, n = 23, 1024, 30_007
+    rng = np.random.default_rng(77)
+    m = (1 << w) - 1
+    codes, packed = column(n, w, seed=4242)
+    lo = rng.integers(0, m + 1, size=K, dtype=np.uint64)
+    hi = np.minimum(lo + rng.integers(0, (m + 1) // 16, size=K, dtype=np.uint64), m)
+    lo[511], hi[511] = lo[512], hi[512]                  # duplicates across a group boundary
+    lo[255], hi[255] = 9, 2                              # an empty one at the end of a group
+    lo[768], hi[768] = 0, m                              # everything, first of a group
+    exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
+    bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi)
+    nb = (n + 7) // 8
+    assert (host(bv)[:, :nb] == exp).all()
+    assert (host(cnt).astype(np.uint64) == ecnt).all()
+
+
 @pytest.mark.parametrize("w,K", [(9, 1024), (17, 1000), (12, 600), (32, 515), (5, 1024)])
 def test_many_predicates(sss, w, K):
     """K > 512 takes the warp-per-block linear kernel and the histogram counts at full width."""
