@@ -443,7 +443,10 @@ struct BlockRows {
         } else {
             const uint32_t e = locator_entry(ix, t >> (32 - kBucketBits));
             uint32_t r = (e & kBucketIdMask) * ix.row_bytes + ix.rows_saddr;
-            if ((t << kBucketBits) > e) r += ix.row_bytes;
+            // one predicated add (ptxas otherwise selects 0 / row_bytes first and adds after)
+            asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}"
+                : "+r"(r)
+                : "r"(t << kBucketBits), "r"(e), "r"(ix.row_bytes));
             row[J] = r;
             flags |= e;
         }
