@@ -110,6 +110,17 @@ __device__ __forceinline__ void store_row_piece(uint8_t* dst, const uint32_t (&w
     }
 }
 
+// Word at byte offset `off` from `base`, the 64-bit address formed by ONE IMAD.WIDE on the FMA pipe
+// (the wide kernel is bound by the ALU pipe, where a 64-bit add takes two instructions; the
+// multiplier 1 comes from constant memory so that ptxas cannot turn it back into the add pair)
+static __constant__ uint32_t c_one = 1u;
+__device__ __forceinline__ uint32_t ldg_u32_at(const uint8_t* base, uint32_t off)
+{
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(off), "r"(c_one), "l"(base));
+    return __ldg(reinterpret_cast<const uint32_t*>(a));
+}
+
 // interval id of code `j` (runtime) of a block whose W words start at `blk` in shared memory
 template <int W>
 __device__ __forceinline__ uint32_t code_id_runtime(const uint32_t* blk, uint32_t j, const PredIndexView& ix)
@@ -162,6 +173,8 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
     const bool vec4 = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
     const int my_col = (int)lane < cols ? (int)lane : 0;   // lanes past the last column idle along
     const int kk = K - 32 * (int)lane;                      // predicates in my column (<= 0: none)
+    // rows read from global memory (through L1): my column of row 0
+    const uint8_t* g_col = reinterpret_cast<const uint8_t*>(ix.masks) + 4 * my_col;
 
     uint32_t iter = 0;
     for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
@@ -179,8 +192,13 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
             uint32_t m[32];
             const uint32_t row_off = id * ix.row_bytes + rows_base;  // my code's mask row
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-                m[j] = row_mask_word<kSmem>(ix, __shfl_sync(0xFFFFFFFFu, row_off, j), 4 * my_col);
+            for (int j = 0; j < 32; j++) {
+                const uint32_t r = __shfl_sync(0xFFFFFFFFu, row_off, j);
+                // (measured: the IMAD.WIDE address pays from 16 bit on, 0.66 -> 0.69 of the HBM peak at
+                //  K = 1024, and costs two points below, where the ring is three stages deep)
+                if constexpr (kSmem || W < 16) m[j] = row_mask_word<kSmem>(ix, r, 4 * my_col);
+                else m[j] = ldg_u32_at(g_col, r);
+            }
             if (valid != 32) {  // only the column's last block: codes past n contribute zero bits
 #pragma unroll
                 for (int j = 0; j < 32; j++)
