@@ -110,17 +110,6 @@ __device__ __forceinline__ void store_row_piece(uint8_t* dst, const uint32_t (&w
     }
 }
 
-// Word at byte offset `off` from `base`, the 64-bit address formed by ONE IMAD.WIDE on the FMA pipe
-// (the wide kernel is bound by the ALU pipe, where a 64-bit add takes two instructions; the
-// multiplier 1 comes from constant memory so that ptxas cannot turn it back into the add pair)
-static __constant__ uint32_t c_one = 1u;
-__device__ __forceinline__ uint32_t ldg_u32_at(const uint8_t* base, uint32_t off)
-{
-    uint64_t a;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(off), "r"(c_one), "l"(base));
-    return __ldg(reinterpret_cast<const uint32_t*>(a));
-}
-
 // interval id of code `j` (runtime) of a block whose W words start at `blk` in shared memory
 template <int W>
 __device__ __forceinline__ uint32_t code_id_runtime(const uint32_t* blk, uint32_t j, const PredIndexView& ix)
@@ -197,7 +186,7 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
                 // (measured: the IMAD.WIDE address pays from 16 bit on, 0.66 -> 0.69 of the HBM peak at
                 //  K = 1024, and costs two points below, where the ring is three stages deep)
                 if constexpr (kSmem || W < 16) m[j] = row_mask_word<kSmem>(ix, r, 4 * my_col);
-                else m[j] = ldg_u32_at(g_col, r);
+                else m[j] = __ldg(reinterpret_cast<const uint32_t*>(ptr_add_fma(g_col, r)));
             }
             if (valid != 32) {  // only the column's last block: codes past n contribute zero bits
 #pragma unroll

@@ -532,6 +532,19 @@ __device__ __forceinline__ uint32_t bit_select(uint32_t a, uint32_t b, uint32_t 
 #endif
 static __constant__ uint32_t c_shr_mul[5] = {0u, 1u << 31, 1u << 30, 0u, 1u << 28};  // [S] = 2^(32 - S), S = 1, 2, 4
 
+// base + off as ONE IMAD.WIDE on the FMA pipe.  ptxas forms a 64-bit address with two instructions
+// (IADD3 + carry add; `p + k * stride` with a constant k even with three), most of them on the ALU pipe
+// these kernels are short of; the multiplier 1 is loaded from constant memory so that it cannot be
+// folded back into the add pair.
+static __constant__ uint32_t c_one = 1u;
+template <class T>
+__device__ __forceinline__ T* ptr_add_fma(T* base, uint32_t off_bytes)
+{
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(off_bytes), "r"(c_one), "l"(base));
+    return reinterpret_cast<T*>(a);
+}
+
 // one exchange stage on a register pair: swaps the high S-bit groups of `lo` with the low ones of `hi`
 template <int S>
 __device__ __forceinline__ void exchange_bits(uint32_t& lo, uint32_t& hi)
