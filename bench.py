@@ -16,12 +16,17 @@ e2e     = the same sweep through the host-buffer C-ABI call the C++ drop-in laye
           (sss_host_scan_range: pinned host buffers, H2D + kernel + D2H inside the timed region)
 roofline= algorithmic bytes (w/8 + 1/8 per code) / measured kernel time vs. MEASURED_PEAKS.json hbm_gbs
 cpu_baseline / --impl reference = the reference's own AVX2 scan (oracle/_ref) on the host cores.
-Extra keys (per_width, shared, unpack) carry the per-bit-width and per-K numbers the metric asks for.
+The line stays compact (< 6 KB, same keys at every N): `summary` carries a handful of per-K numbers
+(shared scan K = 64 at 17 / 23 bit, linear K = 1024 at 9 bit, cfg 5's sharded shared scan with its count
+all-reduce, ...), `per_width_frac` the 32 per-width roofline fractions; the full tables (per_width,
+shared_sweep, unpack, pack, positions, calibration, cfg1 CUDA-graph timing, cfg4 at 2^30 codes, the CPU
+reference detail) go to the side file named by `extras_file` (gpurun_out/bench_extras_N<gpus>.json).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -124,6 +129,25 @@ class ClockSampler:
 # reference arm / cpu baseline (the ONLY places that execute anything under oracle/)
 # ---------------------------------------------------------------------------------------------
 
+_cpu_columns = {}
+
+
+def _cpu_column(w, logn, seed=42):
+    """Uniform-random packed column on the host (uniform bits == uniform codes), cached per (w, logn)
+    so that the steps of one run scan the same data instead of regenerating 4 GiB of it per step."""
+    import numpy as np
+    from oracle import binding as B
+    key = (w, logn)
+    if key not in _cpu_columns:
+        n = 1 << logn
+        rng = np.random.default_rng(seed + w)
+        packed = np.zeros(B.compressed_buffer_size(w, n), dtype=np.uint8)
+        payload = n * w // 8
+        packed[:payload] = np.frombuffer(rng.bytes(payload), dtype=np.uint8)
+        _cpu_columns[key] = packed
+    return _cpu_columns[key]
+
+
 def cpu_reference_sweep(logn, reps, threads):
     """The reference's own CPU scan over a bounded sample: 2^logn uniform codes per width.
 
@@ -132,21 +156,17 @@ def cpu_reference_sweep(logn, reps, threads):
     16 bits); every host thread scans its own range of the column.  If
     oracle/_ref is absent the plain-C oracle port is timed instead (kind "port").
     Returns (codes_per_s over the whole sweep, per-width seconds, kind)."""
-    import numpy as np
+    import ctypes as C
+
     from oracle import binding as B
     n = 1 << logn
-    rng = np.random.default_rng(42)
     per_w = {}
     kind = "reference" if all(B.ref_available(w) for w in WIDTHS) else "port"
     for w in WIDTHS:
-        nbytes = B.compressed_buffer_size(w, n)
-        packed = np.zeros(nbytes, dtype=np.uint8)
-        payload = n * w // 8
-        packed[:payload] = np.frombuffer(rng.bytes(payload), dtype=np.uint8)  # uniform bits == uniform codes
+        packed = _cpu_column(w, logn)
         key = 3 & ((1 << w) - 1)  # the reference only has equality predicates (src/simd_scan.cpp:47)
         if kind == "reference":
             variant = B.SCAN["256_unrolled"] if w <= 16 else B.SCAN["128_unrolled"]
-            import ctypes as C
             hits = C.c_longlong(0)
             s = B.ref(w).ref_time_scan(variant, key, packed.ctypes.data, n, threads, reps, C.byref(hits))
         else:
@@ -154,6 +174,25 @@ def cpu_reference_sweep(logn, reps, threads):
         per_w[w] = s
     total = sum(per_w.values())
     return len(WIDTHS) * n / total, per_w, kind
+
+
+def cpu_reference_shared(threads, w=17, K=64, logn=22, reps=2):
+    """The reference's shared scans (K equality predicates, one pass) on the host cores, column
+    range-partitioned over the threads -- the CPU side of `e2e_shared`.  None when oracle/_ref is absent."""
+    import numpy as np
+    from oracle import binding as B
+    if not B.ref_available(w):
+        return None
+    n = 1 << logn
+    packed = _cpu_column(w, logn, seed=7)
+    keys = np.ascontiguousarray(np.random.default_rng(7).integers(0, 1 << w, size=K), dtype=np.int32)
+    sec_std = B.ref(w).ref_time_shared_scan(B.SHARED["128_standard"], keys.ctypes.data, K, packed.ctypes.data, n,
+                                            threads, reps)
+    sec_lin = B.ref(w).ref_time_shared_scan_linear(B.LINEAR["linear_standard"], keys.ctypes.data, K,
+                                                   packed.ctypes.data, n, threads, reps)
+    return {"w": w, "K": K, "log2_n": logn, "threads": threads,
+            "shared_scan_128_standard_codes_per_s": n / sec_std,
+            "shared_scan_128_linear_standard_codes_per_s": n / sec_lin}
 
 
 def cpu_reference_detail(threads):
@@ -215,9 +254,9 @@ def run_reference_arm(args):
         return 0
     threads = os.cpu_count() or 1
     logn = args.ref_logn
-    # warm-up + timed steps: each step = the sweep over the bounded sample
+    # warm-up + timed steps: each step = the sweep over the bounded sample (columns generated once)
     for _ in range(args.warmup):
-        cpu_reference_sweep(min(logn, 22), 1, threads)
+        cpu_reference_sweep(logn, 1, threads)
     t_steps = []
     kind = "port"
     for _ in range(args.steps):
@@ -237,6 +276,15 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "codes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if kind == "reference" and not args.no_extras:
+        # the CPU side of the product arm's `e2e_shared` (shared scan, K = 64 equality predicates, 17 bit)
+        sh = cpu_reference_shared(threads)
+        if sh:
+            line["e2e_shared"] = {"value": max(sh["shared_scan_128_standard_codes_per_s"],
+                                               sh["shared_scan_128_linear_standard_codes_per_s"]),
+                                  "unit": "codes/s", "workload": "shared scan K=64, 17 bit (best of the reference's "
+                                  "shared_scan_128_standard / _linear_standard)", **{k: (round(v, 1) if isinstance(v, float) else v)
+                                                                                   for k, v in sh.items()}}
     emit(line)
     return 0
 
@@ -253,89 +301,187 @@ def workload_config(args):
 # our arm
 # ---------------------------------------------------------------------------------------------
 
-def run_cfg5(args):
-    """Optional workload (not the contract line): BASELINE configs[4] -- shared scan, K = 64 range
-    predicates over 23-bit codes, the column range-sharded over the ranks (2^31 codes per GPU = 16 Gi
-    codes on 8 GPUs), per-query counts combined with one NCCL all-reduce.  `--workload cfg5`."""
-    import torch
-    import torch.distributed as dist
+class Dist:
+    """The multi-rank plumbing of one bench process (one process per GPU, torch.distributed/NCCL)."""
 
-    from shared_simd_scan_b200 import api
-    from shared_simd_scan_b200 import dist as sdist
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: shared_simd_scan_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        else:
+            self.dist = None
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w, K = 23, 64
-    n_per = 1 << args.cfg5_logn
-    shard = sdist.generate_shard(n_per * world, w, seed=42 + w)
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def all_reduce(self, t):
+        if self.dist:
+            self.dist.all_reduce(t)
+        return t
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t)
+        return float(t.item())
+
+    def close(self):
+        if self.dist:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def random_ranges(torch, w, K, seed):
+    """K uniform-random ranges: lo uniform, width uniform in [0, 2 * 2^w / K)."""
     m = (1 << w) - 1
-    g = torch.Generator().manual_seed(42)
+    g = torch.Generator().manual_seed(seed)
     lo = torch.randint(0, m + 1, (K,), generator=g)
-    hi = torch.clamp(lo + torch.randint(0, 2 * (m + 1) // K, (K,), generator=g), max=m)
-    lo_d, hi_d = lo.to(torch.int32).cuda(), hi.to(torch.int32).cuda()
+    hi = torch.clamp(lo + torch.randint(0, max(2, 2 * (m + 1) // K), (K,), generator=g), max=m)
+    return lo.to(torch.int32).cuda(), hi.to(torch.int32).cuda()
+
+
+def measure_cfg5(D, api, logn, steps, peak):
+    """BASELINE configs[4]: shared scan, K = 64 range predicates over 23-bit codes, the global column
+    range-sharded over the ranks (2^logn codes per GPU; 2^31 x 8 GPUs = 16 Gi codes), per-query counts
+    combined with ONE NCCL all-reduce inside the timed region.  Checks the all-reduced counts against
+    the per-rank counts and every rank's count 0 against the popcount of its own bitvector 0."""
+    torch = D.torch
+    from shared_simd_scan_b200 import dist as sdist
+    w, K = 23, 64
+    shard = sdist.generate_shard((1 << logn) * D.world, w, seed=42 + w)
+    lo_d, hi_d = random_ranges(torch, w, K, seed=42)
     out = torch.empty((K, (api.bitvec_bytes(shard.count) + 127) // 128 * 128), dtype=torch.uint8, device="cuda")
     counts = torch.empty(K, dtype=torch.int64, device="cuda")
 
     def step():
         api.shared_scan(shard.packed, shard.count, w, lo_d, hi_d, out=out, counts=counts)
-        if world > 1:
-            dist.all_reduce(counts)
+        D.all_reduce(counts)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    # correctness of the collective: global == sum of locals; local count 0 == popcount of bitvector 0
+    api.shared_scan(shard.packed, shard.count, w, lo_d, hi_d, out=out, counts=counts)
+    local = counts.clone()
+    words = out[0, : shard.count // 8].view(torch.int64)
+    pop0 = 0
+    for part in words.split(1 << 24):  # SWAR popcount, chunked to bound the temporaries
+        x = part.clone()
+        x = x - ((x >> 1) & 0x5555555555555555)
+        x = (x & 0x3333333333333333) + ((x >> 2) & 0x3333333333333333)
+        x = (x + (x >> 4)) & 0x0F0F0F0F0F0F0F0F
+        pop0 += int(((x * 0x0101010101010101) >> 56 & 0xFF).sum().item())
+    assert pop0 == int(local[0].item()), "cfg5: count 0 != popcount of bitvector 0"
+    D.all_reduce(counts)
+    if D.dist:
+        gathered = [torch.empty_like(local) for _ in range(D.world)]
+        D.dist.all_gather(gathered, local)
+        assert torch.equal(torch.stack(gathered).sum(0), counts), "cfg5: all-reduced counts != sum of per-rank counts"
+    for _ in range(3):
         step()
-    barrier()
+    D.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     b.record()
-    barrier()
-    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / args.steps
-    peak, _ = measured_peak()
+    D.barrier()
+    ms = D.max_over_ranks(a.elapsed_time(b)) / steps
     bytes_per_gpu = shard.count * (w / 8 + K / 8)
-    if rank == 0:
-        emit({
-            "workload": f"cfg5: shared scan K=64 over {world} x 2^{args.cfg5_logn} 23-bit codes, range-sharded, "
-                        "NCCL all-reduce of the 64 counts", "n_gpus": world, "steps": args.steps, "ms_per_step": ms,
-            "value": world * shard.count / (ms * 1e-3), "unit": "codes/s", "scaling": "weak",
-            "per_gpu_gb_per_s": round(bytes_per_gpu / ms / 1e6, 1),
-            "per_gpu_frac_of_measured_peak": round(bytes_per_gpu / ms / 1e6 / peak, 4),
-            "global_count_of_query_0": int(counts[0].item())})
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    res = {"w": w, "K": K, "log2_n_per_gpu": logn, "ms": round(ms, 4),
+           "gcodes_per_s": round(D.world * shard.count / ms / 1e6, 1),
+           "gb_per_s_per_gpu": round(bytes_per_gpu / ms / 1e6, 1),
+           "frac": round(bytes_per_gpu / ms / 1e6 / peak, 4), "allreduce_in_timed_region": D.world > 1,
+           "count0": int(counts[0].item())}
+    del out, shard
+    return res
+
+
+def measure_e2e_scan(D, api, columns, n, e2e_steps):
+    """The contract's e2e: the 32-width sweep through sss_host_scan_range from pinned host memory
+    (H2D copy of every column + kernel + D2H of bitvector and count inside the timed region)."""
+    torch = D.torch
+    h_in = api.pinned_empty(api.packed_bytes(n, 32))
+    h_out = api.pinned_empty(api.bitvec_bytes(n))
+    e2e_sec, h2d, d2h, counts = [], 0, 0, []
+    for s in range(e2e_steps + 1):  # first pass = warm-up (staging buffers get allocated)
+        sec = 0.0
+        h2d = d2h = 0
+        for w in WIDTHS:
+            nb = api.packed_bytes(n, w)
+            h_in[:nb].copy_(columns[w][:nb])  # refill the host column (untimed)
+            torch.cuda.synchronize()
+            lo, hi = predicate(w)
+            t0 = time.perf_counter()
+            _, c = api.host_scan(h_in, n, w, lo, hi, tail_granule=1, out=h_out)
+            sec += time.perf_counter() - t0
+            h2d += (n // 32) * w * 4
+            d2h += n // 8 + 8
+            if s == e2e_steps:
+                counts.append(c)
+        if s > 0:
+            e2e_sec.append(sec)
+    sec = D.max_over_ranks(statistics.mean(e2e_sec))
+    del h_in, h_out
+    return {"value": D.world * len(WIDTHS) * n / sec, "unit": "codes/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "steps": e2e_steps, "h2d_gb_per_s_per_gpu": round(h2d / sec / 1e9, 1),
+            "api": "sss_host_scan_range (pinned host buffers, 64 MiB chunks, 3 streams)"}, counts
+
+
+def measure_e2e_shared(D, api, columns, n, steps, w=17, K=64):
+    """e2e of BASELINE configs[2]: shared scan, K = 64 range predicates over 2^30 17-bit codes through
+    sss_host_shared_scan (host column in, K host bitvectors + counts out, all copies timed)."""
+    import numpy as np
+    torch = D.torch
+    lo_d, hi_d = random_ranges(torch, w, K, seed=42 + K)
+    lo_h = lo_d.cpu().numpy().view(np.uint32).copy()
+    hi_h = hi_d.cpu().numpy().view(np.uint32).copy()
+    nb = api.packed_bytes(n, w)
+    h_in = api.pinned_empty(nb)
+    h_in.copy_(columns[w][:nb])
+    stride = (api.bitvec_bytes(n) + 127) // 128 * 128
+    h_out = api.pinned_empty(K * stride)
+    h_cnt = np.zeros(K, dtype=np.uint64)
+    torch.cuda.synchronize()
+    secs = []
+    for s in range(steps + 1):
+        t0 = time.perf_counter()
+        api.host_shared_scan_into(h_in, n, w, lo_h, hi_h, h_out, stride, h_cnt)
+        if s > 0:
+            secs.append(time.perf_counter() - t0)
+    sec = D.max_over_ranks(statistics.mean(secs))
+    # same counts as the device-resident call
+    _, cnt = api.shared_scan(columns[w], n, w, lo_d, hi_d)
+    assert (cnt.cpu().numpy().astype(np.uint64) == h_cnt).all(), "e2e_shared: host path != device path counts"
+    del h_in, h_out
+    return {"value": D.world * n / sec, "unit": "codes/s", "workload": f"shared scan K={K}, {w} bit, 2^{int(math.log2(n))} codes per GPU",
+            "h2d_bytes_per_step": (n // 32) * w * 4, "d2h_bytes_per_step": K * (n // 8) + 8 * K, "steps": steps,
+            "d2h_gb_per_s_per_gpu": round(K * (n // 8) / sec / 1e9, 1), "api": "sss_host_shared_scan (pinned)"}
 
 
 def run_ours(args):
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
-    import torch.distributed as dist
 
     from shared_simd_scan_b200 import api
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: shared_simd_scan_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D = Dist()
+    rank, world, local = D.rank, D.world, D.local
     n = 1 << args.logn
     peak, peak_src = measured_peak()
 
@@ -349,44 +495,46 @@ def run_ours(args):
         for i, w in enumerate(WIDTHS):
             lo, hi = predicate(w)
             api.scan(columns[w], n, w, lo, hi, out=bitvec, count=counts[i:i + 1])
-        if world > 1:
-            dist.all_reduce(counts)  # the only collective on the path: 32 x int64
+        D.all_reduce(counts)  # the only collective on the path: 32 x int64
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         step()
-    barrier()
+    D.barrier()
 
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    D.barrier()
     wall0 = time.perf_counter()
     t_begin.record()
     for k in range(args.steps):
         step()
     t_end.record()
-    barrier()
+    D.barrier()
     wall1 = time.perf_counter()
     clocks = sampler.stop(wall0, wall1)
-    dev_ms = t_begin.elapsed_time(t_end)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    ms_per_step = dev_ms / args.steps
+    ms_per_step = D.max_over_ranks(t_begin.elapsed_time(t_end)) / args.steps
     value = world * len(WIDTHS) * n / (ms_per_step * 1e-3)
 
     # roofline of the step's kernel (32 launches of scan_range_kernel<W>): algorithmic bytes of a step over the
     # device time of a step, both from the timed region above (so launch gaps count against the kernel)
     total_bytes = sum(n * (w / 8 + 1 / 8) for w in WIDTHS)
     achieved = total_bytes / (ms_per_step * 1e-3) / 1e9
-    final_counts = counts.cpu().tolist()
+
+    # the collective is right: the all-reduced counts are the sum of the ranks' own counts
+    local_counts = torch.zeros(len(WIDTHS), dtype=torch.int64, device="cuda")
+    for i, w in enumerate(WIDTHS):
+        lo, hi = predicate(w)
+        api.scan(columns[w], n, w, lo, hi, out=bitvec, count=local_counts[i:i + 1])
+    final_counts = local_counts.cpu().tolist()
+    if D.dist:
+        gathered = [torch.empty_like(local_counts) for _ in range(world)]
+        D.dist.all_gather(gathered, local_counts)
+        assert torch.equal(torch.stack(gathered).sum(0), counts), "all-reduced counts != sum of per-rank counts"
+    else:
+        assert torch.equal(local_counts, counts)
 
     # per-width launch duration, after the timed region: `reps` back-to-back launches of one width between
     # two events on the launching stream (an event pair around a single 50 us launch would add ~20 %)
@@ -407,80 +555,197 @@ def run_ours(args):
                           "gb_per_s": round(nb / ms / 1e6, 1), "frac_of_measured_peak": round(nb / ms / 1e6 / peak, 4),
                           "frac_of_8TBps": round(nb / ms / 1e6 / 8000.0, 4)})
 
-    # ---- e2e: the host-buffer C-ABI call (what include/simd_scan.hpp wraps), pinned host memory ----
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    max_bytes = api.packed_bytes(n, 32)
-    h_in = api.pinned_empty(max_bytes)
-    h_out = api.pinned_empty(api.bitvec_bytes(n))
-    e2e_sec, h2d, d2h = [], 0, 0
-    e2e_counts = []
-    for s in range(e2e_steps + 1):  # first pass = warm-up (staging buffers get allocated)
-        sec = 0.0
-        h2d = d2h = 0
-        for w in WIDTHS:
-            nb = api.packed_bytes(n, w)
-            h_in[:nb].copy_(columns[w][:nb])  # refill the host column (untimed)
-            torch.cuda.synchronize()
-            lo, hi = predicate(w)
-            t0 = time.perf_counter()
-            _, c = api.host_scan(h_in, n, w, lo, hi, tail_granule=1, out=h_out)
-            sec += time.perf_counter() - t0
-            h2d += (n // 32) * w * 4
-            d2h += n // 8 + 8
-            if s == e2e_steps:
-                e2e_counts.append(c)
-        if s > 0:
-            e2e_sec.append(sec)
-    te = torch.tensor([statistics.mean(e2e_sec)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * len(WIDTHS) * n / float(te.item())
-    del h_in, h_out
+    # ---- e2e: the host-buffer C-ABI calls (what include/simd_scan.hpp wraps), pinned host memory ----
+    e2e_steps = max(1, args.e2e_steps)
+    e2e, e2e_counts = measure_e2e_scan(D, api, columns, n, e2e_steps)
     if world == 1:
         assert e2e_counts == final_counts, "host-buffer path and device-resident path disagree on the match counts"
+    e2e_shared = measure_e2e_shared(D, api, columns, n, e2e_steps) if not args.no_extras else None
 
+    # ---- the compact per-K summary, at every N (per-GPU device-resident numbers: max time over ranks) ----
+    summary = {}
+    extras_out = {"per_width": per_width}
+    if not args.no_extras:
+        summary["cfg5_shared_k64_w23"] = measure_cfg5(D, api, min(args.cfg5_logn, args.logn + 1), 5, peak)
+        for kind, w, K in (("shared", 17, 64), ("linear", 9, 64), ("shared", 17, 8)):
+            summary[f"{kind}_k{K}_w{w}"] = shared_point(D, api, columns, n, kind, w, K, peak)
+    fr = [p["frac_of_measured_peak"] for p in per_width]
+    summary["scan_frac_min"] = {"w": WIDTHS[fr.index(min(fr))], "frac": min(fr)}
+    summary["scan_widths_below_0.95"] = [p["w"] for p in per_width if p["frac_of_measured_peak"] < 0.95]
+
+    traffic, _ = captured_traffic()
     line = {
         "metric": "scanned_codes_per_s", "value": value, "unit": "codes/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "codes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "sss_host_scan_range (pinned host buffers, 64 MiB chunks, 3 streams)"},
+        "clocks": clocks, "e2e": e2e, "e2e_shared": e2e_shared,
         "gpu_launches": args.steps * len(WIDTHS),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4),
-                     "traffic": captured_traffic()[0] if args.logn == 30 else None,
-                     "algorithmic_bytes": total_bytes,
-                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 32 launches of "
-                                       "one step at 2^30 codes (profiles/r01_scan_traffic.json)",
-                     "peak_source": peak_src,
-                     "kernel": "sss::scan_range_kernel<W> (W = 1: scan_direct_kernel), the 32 launches of a step: "
-                               "bytes = sum of n*(w/8+1/8), time = the step's device time in the timed region "
-                               "(per-width launch durations in per_width: 10 back-to-back launches per event pair)",
+                     "frac": round(achieved / peak, 4), "traffic": traffic if args.logn == 30 else None,
+                     "algorithmic_bytes": total_bytes, "peak_source": peak_src,
+                     "traffic_source": "ncu dram bytes of the step's 32 launches, profiles/r01_scan_traffic.json",
+                     "kernel": "sss::scan_range_kernel<W>, the 32 launches of a step (W = 1: scan_direct_kernel); "
+                               "bytes = sum n*(w/8+1/8), time = the step's device time in the timed region",
                      "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},
-        "per_width": per_width,
+        "per_width_frac": [round(f, 3) for f in fr],
+        "summary": summary,
     }
 
+    # ---- the full tables: measured on rank 0 of a single-GPU run, written to the side file ----
     if rank == 0 and world == 1 and not args.no_extras:
-        line.update(extras(args, api, columns, n, peak))
-    if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
+        extras_out.update(extras(args, api, columns, n, peak))
+    threads = os.cpu_count() or 1
+    if rank == 0 and not args.no_cpu:
+        # bounded CPU sample; smaller when other ranks are waiting (the full sample runs at N = 1)
+        cpu_logn = args.cpu_logn if world == 1 else min(args.cpu_logn, 24)
         t0 = time.perf_counter()
-        v, per_w, kind = cpu_reference_sweep(args.cpu_logn, 2, threads)
+        v, per_w, kind = cpu_reference_sweep(cpu_logn, 2, threads)
         line["cpu_baseline"] = {
             "value": v, "unit": "codes/s", "cores": threads, "kind": kind,
-            "sample": f"same sweep on 2^{args.cpu_logn} uniform codes per width (best of 2), equality key 3; "
+            "sample": f"same sweep on 2^{cpu_logn} uniform codes per width (best of 2), equality key 3; "
                       "scan_256_unrolled (w<=16) / scan_128_unrolled (w>16) of the unmodified reference, column "
                       f"range-partitioned over {threads} host threads; {time.perf_counter() - t0:.1f} s of wall time"}
-        line["cpu_reference_detail"] = cpu_reference_detail(threads)
-    elif rank == 0:
+        if world == 1 and not args.no_extras:
+            extras_out["cpu_reference_detail"] = cpu_reference_detail(threads)
+            sh = cpu_reference_shared(threads)
+            if sh and e2e_shared:
+                e2e_shared["cpu_reference_codes_per_s"] = round(
+                    max(sh["shared_scan_128_standard_codes_per_s"], sh["shared_scan_128_linear_standard_codes_per_s"]), 1)
+    else:
         line["cpu_baseline"] = None
+    # cfg 4 at its stated size needs the GPU to itself: free the sweep's columns first
+    if rank == 0 and world == 1 and not args.no_extras and args.logn == 30 and not args.no_cfg4:
+        keep9 = columns[9]
+        columns.clear()
+        del bitvec
+        torch.cuda.empty_cache()
+        extras_out["cfg4"] = measure_cfg4(torch, api, keep9, n, peak)
+        summary["linear_k1024_w9_cfg4"] = {k: extras_out["cfg4"][k] for k in ("log2_n", "chunks", "ms", "gcodes_per_s", "frac")}
     if rank == 0:
+        extras_file = args.extras_file or os.path.join("gpurun_out", f"bench_extras_N{world}.json")
+        try:
+            os.makedirs(os.path.dirname(os.path.join(ROOT, extras_file)) or ".", exist_ok=True)
+            with open(os.path.join(ROOT, extras_file), "w") as f:
+                json.dump({"line": line, **extras_out}, f)
+            line["extras_file"] = extras_file
+        except OSError as e:
+            line["extras_file"] = f"not written: {e}"
         emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     return 0
+
+
+def shared_point(D, api, columns, n, kind, w, K, peak):
+    """One (op, w, K) cell of the metric's table on this run's GPUs: device-resident, best of 5 event
+    pairs, max over ranks."""
+    torch = D.torch
+    lo_d, hi_d = random_ranges(torch, w, K, seed=42 + K)
+    cnt = torch.empty(K, dtype=torch.int64, device="cuda")
+    if kind == "shared":
+        buf = torch.empty((K, (api.bitvec_bytes(n) + 127) // 128 * 128), dtype=torch.uint8, device="cuda")
+        fn = lambda: api.shared_scan(columns[w], n, w, lo_d, hi_d, out=buf, counts=cnt)  # noqa: E731
+    else:
+        buf = torch.empty((4 * ((n + 31) // 32), K), dtype=torch.uint8, device="cuda")
+        fn = lambda: api.shared_scan_linear(columns[w], n, w, lo_d, hi_d, out=buf, counts=cnt)  # noqa: E731
+    ms = D.max_over_ranks(launch_ms(fn))
+    b = n * (w / 8 + K / 8)
+    del buf
+    return {"ms": round(ms, 4), "gcodes_per_s": round(n / ms / 1e6, 1), "gb_per_s": round(b / ms / 1e6, 1),
+            "frac": round(b / ms / 1e6 / peak, 4)}
+
+
+def measure_cfg4(torch, api, column9, n, peak):
+    """BASELINE configs[3] at its stated size: linear shared scan, K = 1024 equality+range predicates over
+    2^30 9-bit codes = 128 GiB of output.  Resident when the GPU has room for it, else in `chunks` equal
+    column chunks that reuse one output region (stated in the result)."""
+    w, K = 9, 1024
+    lo_d, hi_d = random_ranges(torch, w, K, seed=42 + K)
+    cnt = torch.empty(K, dtype=torch.int64, device="cuda")
+    free, _total = torch.cuda.mem_get_info()
+    chunks = 1
+    while chunks < 64 and (n // chunks) // 8 * K + (2 << 30) > free:
+        chunks *= 2
+    nc = n // chunks
+    out = torch.empty(((nc // 8), K), dtype=torch.uint8, device="cuda")
+    bytes_per_chunk_in = nc * w // 8  # a multiple of 16 bytes for these sizes
+
+    def run():
+        for c in range(chunks):
+            api.shared_scan_linear(column9[c * bytes_per_chunk_in:], nc, w, lo_d, hi_d, out=out, counts=cnt)
+
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    a.record()
+    for _ in range(reps):
+        run()
+    b.record()
+    b.synchronize()
+    ms = a.elapsed_time(b) / reps
+    nbytes = n * (w / 8 + K / 8)
+    # the big run's first rows equal a small run of the same kernel family on the same column prefix
+    # (which the parity tests pin against the oracle)
+    ns = 1 << 19
+    small, _ = api.shared_scan_linear(column9[(chunks - 1) * bytes_per_chunk_in:], ns, w, lo_d, hi_d)
+    assert torch.equal(small[: ns // 8], out[: ns // 8]), "cfg4: full-size rows != small-run rows"
+    assert int(cnt.sum().item()) > 0
+    del small
+    res = {"op": "linear", "w": w, "K": K, "log2_n": int(math.log2(n)), "chunks": chunks,
+           "out_gib": round(K * (n // 8) / 2**30, 1), "resident_out_gib": round(K * (nc // 8) / 2**30, 1),
+           "ms": round(ms, 3), "gcodes_per_s": round(n / ms / 1e6, 2), "gb_per_s": round(nbytes / ms / 1e6, 1),
+           "frac": round(nbytes / ms / 1e6 / peak, 4)}
+    del out
+    return res
+
+
+def measure_cfg1(torch, api, peak):
+    """BASELINE configs[0] on the GPU: single range-predicate scan over 2^24 11-bit codes -- a 3.8 us
+    kernel at the HBM roofline, so it is timed as 100 launches captured in ONE CUDA graph (launch
+    latency amortised), and as 100 plain stream launches for comparison."""
+    w, n = 11, 1 << 24
+    col = api.generate_packed(n, w, seed=42 + w)
+    bv = torch.empty(api.bitvec_bytes(n), dtype=torch.uint8, device="cuda")
+    cnt = torch.empty(1, dtype=torch.int64, device="cuda")
+    lo, hi = predicate(w)
+    launches = 100
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            api.scan(col, n, w, lo, hi, out=bv, count=cnt)
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(launches):
+                api.scan(col, n, w, lo, hi, out=bv, count=cnt)
+        for _ in range(2):
+            g.replay()
+        s.synchronize()
+        best_graph = 1e9
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            g.replay()
+            b.record(s)
+            b.synchronize()
+            best_graph = min(best_graph, a.elapsed_time(b) / launches)
+        best_plain = 1e9
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            for _ in range(launches):
+                api.scan(col, n, w, lo, hi, out=bv, count=cnt)
+            b.record(s)
+            b.synchronize()
+            best_plain = min(best_plain, a.elapsed_time(b) / launches)
+    nbytes = n * (w / 8 + 1 / 8)
+    ideal_us = nbytes / (peak * 1e9) * 1e6
+    return {"w": w, "log2_n": 24, "launches_per_graph": launches, "us_per_scan_graph": round(best_graph * 1e3, 2),
+            "us_per_scan_stream": round(best_plain * 1e3, 2), "ideal_us_at_measured_peak": round(ideal_us, 2),
+            "pct_of_ideal_graph": round(100 * ideal_us / (best_graph * 1e3), 1),
+            "gcodes_per_s_graph": round(n / best_graph / 1e6, 1),
+            "note": "25 MB working set: L2-resident after the first launch, so the fraction can exceed the HBM roofline"}
 
 
 def extras(args, api, columns, n, peak):
@@ -500,17 +765,14 @@ def extras(args, api, columns, n, peak):
         b.synchronize()
         return a.elapsed_time(b) / reps
 
-    out = {"shared": [], "unpack": [], "pack": [], "positions": [], "calibration": calibration(api, timed, peak)}
+    out = {"shared": [], "unpack": [], "pack": [], "positions": [], "calibration": calibration(api, timed, peak),
+           "cfg1": measure_cfg1(torch, api, peak)}
     if not args.no_sweep:
         out["shared_sweep"] = shared_sweep(args, api, columns, n, peak)
-    g = torch.Generator().manual_seed(42)
     for kind, w, K, logn in (("shared", 17, 8, 30), ("shared", 17, 64, 30), ("shared", 23, 64, 30),
                              ("linear", 9, 64, 30), ("linear", 9, 1024, 27)):
         nn = 1 << min(logn, args.logn)
-        m = (1 << w) - 1
-        lo = torch.randint(0, m + 1, (K,), generator=g)
-        hi = torch.clamp(lo + torch.randint(0, max(2, 2 * (m + 1) // K), (K,), generator=g), max=m)
-        lo_d, hi_d = lo.to(torch.int32).cuda(), hi.to(torch.int32).cuda()
+        lo_d, hi_d = random_ranges(torch, w, K, seed=42)
         cnt = torch.empty(K, dtype=torch.int64, device="cuda")
         if kind == "shared":
             buf = torch.empty((K, (api.bitvec_bytes(nn) + 127) // 128 * 128), dtype=torch.uint8, device="cuda")
@@ -523,7 +785,8 @@ def extras(args, api, columns, n, peak):
                               "gcodes_per_s": round(nn / ms / 1e6, 2), "gb_per_s": round(b / ms / 1e6, 1),
                               "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4)})
         del buf
-    # ascending position list from the scan's bitvector, at three selectivities (w = 17)
+    # ascending position list from the scan's bitvector, at three selectivities (w = 17); algorithmic
+    # bytes = ONE read of the bitvector + 8 bytes per match
     w = 17
     m = (1 << w) - 1
     bv = torch.empty(api.bitvec_bytes(n), dtype=torch.uint8, device="cuda")
@@ -532,12 +795,16 @@ def extras(args, api, columns, n, peak):
         hi_v = max(0, int(sel * (m + 1)) - 1)
         api.scan(columns[w], n, w, 0, hi_v, out=bv, count=cnt1)
         hits = int(cnt1.item())
-        api.positions(bv, n, capacity=hits)  # sizes the context workspace outside the timed region
-        ms = timed(lambda: api.positions(bv, n, capacity=hits), reps=3, warm=1)
-        b = 2 * n / 8 + 8.0 * hits
+        pos_buf = torch.empty(max(hits, 1), dtype=torch.int64, device="cuda")
+        num_buf = torch.empty(1, dtype=torch.int64, device="cuda")
+        api.positions(bv, n, capacity=hits, out=pos_buf, num=num_buf)  # sizes the context workspace (untimed)
+        ms = timed(lambda: api.positions(bv, n, capacity=hits, out=pos_buf, num=num_buf), reps=5, warm=2)
+        assert int(num_buf.item()) == hits
+        b = n / 8 + 8.0 * hits
         out["positions"].append({"w": w, "n": n, "selectivity": sel, "hits": hits, "ms": round(ms, 4),
                                  "gcodes_per_s": round(n / ms / 1e6, 1), "gb_per_s": round(b / ms / 1e6, 1),
                                  "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4)})
+        del pos_buf
     del bv
     n2 = 1 << min(28, args.logn)
     dec = torch.empty(n2, dtype=torch.int32, device="cuda")
@@ -644,6 +911,20 @@ def shared_sweep(args, api, columns, n, peak):
             "rows": rows}
 
 
+def run_cfg5(args):
+    """`--workload cfg5`: BASELINE configs[4] alone (also part of every default run's `summary`)."""
+    from shared_simd_scan_b200 import api
+    D = Dist()
+    peak, _ = measured_peak()
+    res = measure_cfg5(D, api, args.cfg5_logn, args.steps, peak)
+    if D.rank == 0:
+        emit({"workload": f"cfg5: shared scan K=64 over {D.world} x 2^{args.cfg5_logn} 23-bit codes, range-sharded, "
+                          "NCCL all-reduce of the 64 counts", "n_gpus": D.world, "steps": args.steps,
+              "value": res["gcodes_per_s"] * 1e9, "unit": "codes/s", "scaling": "weak", **res})
+    D.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -651,14 +932,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--logn", type=int, default=30, help="log2 codes per width per GPU (BASELINE: 30)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-logn", type=int, default=27, help="cpu_baseline sample: log2 codes per width")
     ap.add_argument("--ref-logn", type=int, default=26, help="--impl reference sample: log2 codes per width per step")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "cfg5"],
-                    help="sweep = the contract line; cfg5 = optional sharded shared scan (K=64, 23 bit)")
+                    help="sweep = the contract line; cfg5 = the sharded shared scan (K=64, 23 bit) alone")
     ap.add_argument("--cfg5-logn", type=int, default=31, help="cfg5: log2 codes per GPU")
+    ap.add_argument("--extras-file", default=None, help="side file for the full tables (default gpurun_out/bench_extras_N<gpus>.json)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the (w x K) shared-scan table of the extras")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip cfg 4 at its stated size (128 GiB of output)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner,

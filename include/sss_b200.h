@@ -23,9 +23,15 @@
  *  - Counts and positions are 64-bit (the reference's `int hits` overflows past 2^31 codes).
  *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device entry points
  *    only enqueue work; host entry points (sss_host_*) are synchronous.
- *  - A context is not thread-safe: use it from one host thread at a time (one context per thread
- *    is fine), and it serves one shared scan at a time (its predicate index lives in the context).
- *  - Return value: SSS_OK, a negative SSS_ERR_* argument error, or 1000 + cudaError_t.
+ *  - Threads: every entry point takes the context's lock (host entry points for their whole
+ *    synchronous duration, device entry points while they enqueue), so a context may be shared by
+ *    threads -- its calls serialise.  For CONCURRENT calls give every thread its own context (the C++
+ *    drop-in layer, csrc/host/simd_scan_host.cpp, keeps a pool; the reference's functions are stateless,
+ *    src/simd_scan.cpp:103-158).  A context serves one shared scan / one position pass at a time per
+ *    stream order: its predicate index and look-back workspace live in the context, so device entry
+ *    points of ONE context must be enqueued on one stream (or on streams the caller orders).
+ *  - Return value: SSS_OK, a negative SSS_ERR_* argument error, 1000 + cudaError_t, or (multi-GPU entry
+ *    points) 2000 + ncclResult_t.
  *    There is no CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef SSS_B200_H
@@ -43,6 +49,7 @@ extern "C" {
 #define SSS_ERR_UNSUPPORTED (-2)
 #define SSS_ERR_NO_DEVICE (-3)
 #define SSS_ERR_CUDA_BASE 1000 /* 1000 + cudaError_t */
+#define SSS_ERR_NCCL_BASE 2000 /* 2000 + ncclResult_t (multi-GPU entry points) */
 
 /* tail_granule values of the host entry points: how far past code n-1 the reference variant being
  * replaced keeps evaluating the predicate on the buffer padding. */
@@ -99,6 +106,13 @@ int sss_scan_range(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32
  * (may exceed `capacity`, only the first `capacity` are written). */
 int sss_positions(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base,
                   uint64_t* d_positions, uint64_t capacity, uint64_t* d_num, void* stream);
+
+/* The north star's scan output in one call: bitvector + match count (sss_scan_range) and the ascending
+ * position list of the matches (sss_positions; the position pass reads the bitvector the scan has just
+ * written).  *d_count = number of matches; positions beyond `capacity` are not written. */
+int sss_scan_range_positions(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32_t lo, uint32_t hi,
+                             void* d_bitvec, uint64_t* d_count, uint64_t base, uint64_t* d_positions,
+                             uint64_t capacity, void* stream);
 
 /* Downstream consumers of a scan result (the reference stops at the bitvector).
  * Combine two bitvectors over the first n bits: op = SSS_OP_AND / OR / ANDNOT (a & ~b) / XOR; writes
@@ -162,11 +176,65 @@ int sss_host_shared_scan_linear(sss_ctx* ctx, const void* h_packed, uint64_t n, 
                                 const uint32_t* h_lo, const uint32_t* h_hi, int K, int tail_granule,
                                 void* h_out, uint64_t* h_counts);
 int sss_host_pack(sss_ctx* ctx, const uint32_t* h_codes, uint64_t n, int w, void* h_packed);
+/* Ascending positions (+ base) of the set bits among the first n bits of a HOST bitvector, expanded on
+ * the device; *h_num = how many exist, at most `capacity` are written. */
+int sss_host_positions(sss_ctx* ctx, const void* h_bitvec, uint64_t n, uint64_t base, uint64_t* h_positions,
+                       uint64_t capacity, uint64_t* h_num);
 
 void* sss_host_alloc(size_t bytes); /* pinned host memory, NULL on failure */
 void sss_host_free(void* p);
 int sss_host_register(void* p, size_t bytes);
 int sss_host_unregister(void* p);
+
+/* ---- multi-GPU entry points (the reference is single-device) --------
+ * One process drives N GPUs.  The column is RANGE-partitioned: shard g holds codes
+ * [first_g, first_g + count_g) of the global column (sss_shard_range: every shard but the last is a
+ * multiple of 128 codes, so each starts 16-byte aligned in the packed stream for any width and on a
+ * byte boundary of every bitvector).  Every GPU scans its own shard with the single-GPU kernels on its
+ * own stream; the per-query match counts are combined with ONE ncclAllReduce(sum, uint64 x K) over
+ * NVLink; position lists are rebased by first_g, so the shards' lists in device order are globally
+ * ascending.  No column data crosses GPUs.  Contrast: the reference's only parallel variant partitions
+ * the predicates over OpenMP threads and re-reads the column per predicate (src/simd_scan_shared.cpp:25-32).
+ * NCCL (libnccl.so.2) is loaded at run time and only when N > 1.
+ * Device entry points enqueue on the shards' streams (sss_mgpu_stream) and return; sss_mgpu_sync waits.
+ * Array arguments have one entry per shard, in shard order. */
+#define SSS_MGPU_MAX_DEVICES 16
+typedef struct sss_mgpu sss_mgpu;
+
+int sss_mgpu_create(int n_devices, const int* devices /* NULL: 0..n_devices-1 */, sss_mgpu** out);
+int sss_mgpu_destroy(sss_mgpu* m);
+int sss_mgpu_device_count(const sss_mgpu* m);
+int sss_mgpu_device(const sss_mgpu* m, int shard);      /* CUDA ordinal of the shard's GPU */
+sss_ctx* sss_mgpu_ctx(sss_mgpu* m, int shard);          /* the shard's single-GPU context (pack, generate, ...) */
+void* sss_mgpu_stream(sss_mgpu* m, int shard);          /* cudaStream_t the shard's work is enqueued on */
+int sss_mgpu_sync(sss_mgpu* m);
+
+/* Pure arithmetic: the contiguous range partition of n_global codes into n_shards shards. */
+int sss_shard_range(uint64_t n_global, int n_shards, int shard, uint64_t* first, uint64_t* count);
+
+/* scan_* over the global column.  d_packed[g] / d_bitvec[g]: shard g's packed codes / its slice of the
+ * bitvector, on GPU g.  d_count[g] (one uint64 on GPU g, required) receives the GLOBAL match count on
+ * every GPU.  Optional position lists: d_positions[g] (capacity[g] entries, on GPU g) receives shard g's
+ * matches as GLOBAL code indices, ascending; d_num_local[g] (optional) = how many shard g has. */
+int sss_mgpu_scan_range(sss_mgpu* m, const void* const* d_packed, uint64_t n_global, int w, uint32_t lo, uint32_t hi,
+                        void* const* d_bitvec, uint64_t* const* d_count, uint64_t* const* d_positions,
+                        const uint64_t* capacity, uint64_t* const* d_num_local);
+
+/* shared_scan_* / shared_scan_128_linear_* over the global column: K bounds in HOST memory (replicated to
+ * every GPU), d_out[g] = shard g's K bitvector slices (stride_bytes apart) or, linear != 0, its rows of
+ * the [n/8][K] byte matrix; d_counts[g] (K uint64 on GPU g) receives the GLOBAL per-query counts. */
+int sss_mgpu_shared_scan(sss_mgpu* m, const void* const* d_packed, uint64_t n_global, int w, const uint32_t* h_lo,
+                         const uint32_t* h_hi, int K, int linear, void* const* d_out, uint64_t stride_bytes,
+                         uint64_t* const* d_counts);
+
+/* Host buffers (synchronous): ONE column in host memory; every GPU pulls its own shard over its own
+ * PCIe link (one host thread per GPU), results land in the caller's buffers, counts are summed on the
+ * host.  Same arguments and tail modes as sss_host_scan_range / sss_host_shared_scan. */
+int sss_mgpu_host_scan_range(sss_mgpu* m, const void* h_packed, uint64_t n, int w, uint32_t lo, uint32_t hi,
+                             int tail_granule, void* h_bitvec, uint64_t* h_count);
+int sss_mgpu_host_shared_scan(sss_mgpu* m, const void* h_packed, uint64_t n, int w, const uint32_t* h_lo,
+                              const uint32_t* h_hi, int K, int tail_granule, void* h_bitvecs, uint64_t stride_bytes,
+                              uint64_t* h_counts);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,7 @@ SIGNATURES = {
     "sss_unpack": (_i, [_vp, _vp, _u64, _i, _vp, _vp]),
     "sss_scan_range": (_i, [_vp, _vp, _u64, _i, _u32, _u32, _vp, _vp, _vp]),
     "sss_positions": (_i, [_vp, _vp, _u64, _u64, _vp, _u64, _vp, _vp]),
+    "sss_scan_range_positions": (_i, [_vp, _vp, _u64, _i, _u32, _u32, _vp, _vp, _u64, _vp, _u64, _vp]),
     "sss_bitvec_combine": (_i, [_vp, _i, _vp, _vp, _u64, _vp, _vp, _vp]),
     "sss_unpack_at": (_i, [_vp, _vp, _i, _vp, _u64, _vp, _vp]),
     "sss_calibrate": (_i, [_vp, _i, _vp, _vp, _u64, _u32, _vp]),
@@ -45,6 +46,19 @@ SIGNATURES = {
     "sss_host_shared_scan_ptrs": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "sss_host_shared_scan_linear": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "sss_host_pack": (_i, [_vp, _vp, _u64, _i, _vp]),
+    "sss_host_positions": (_i, [_vp, _vp, _u64, _u64, _vp, _u64, _vp]),
+    "sss_mgpu_create": (_i, [_i, _vp, C.POINTER(_vp)]),
+    "sss_mgpu_destroy": (_i, [_vp]),
+    "sss_mgpu_device_count": (_i, [_vp]),
+    "sss_mgpu_device": (_i, [_vp, _i]),
+    "sss_mgpu_ctx": (_vp, [_vp, _i]),
+    "sss_mgpu_stream": (_vp, [_vp, _i]),
+    "sss_mgpu_sync": (_i, [_vp]),
+    "sss_shard_range": (_i, [_u64, _i, _i, C.POINTER(_u64), C.POINTER(_u64)]),
+    "sss_mgpu_scan_range": (_i, [_vp, _vp, _u64, _i, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "sss_mgpu_shared_scan": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _i, _i, _vp, _u64, _vp]),
+    "sss_mgpu_host_scan_range": (_i, [_vp, _vp, _u64, _i, _u32, _u32, _i, _vp, _vp]),
+    "sss_mgpu_host_shared_scan": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _i, _i, _vp, _u64, _vp]),
     "sss_host_alloc": (_vp, [_sz]),
     "sss_host_free": (None, [_vp]),
     "sss_host_register": (_i, [_vp, _sz]),

@@ -149,17 +149,41 @@ def scan(packed: torch.Tensor, n: int, w: int, lo: int, hi: Optional[int] = None
     return out, count
 
 
-def positions(bitvec: torch.Tensor, n: int, base: int = 0, capacity: Optional[int] = None
+def positions(bitvec: torch.Tensor, n: int, base: int = 0, capacity: Optional[int] = None,
+              out: Optional[torch.Tensor] = None, num: Optional[torch.Tensor] = None
               ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Ascending position list of a bitvector -> (positions int64[capacity], num int64[1])."""
     ctx = Context.current()
     if capacity is None:
-        capacity = n
-    pos = torch.empty(max(capacity, 1), dtype=torch.int64, device=bitvec.device)
-    num = torch.empty(1, dtype=torch.int64, device=bitvec.device)
+        capacity = n if out is None else out.numel()
+    pos = out if out is not None else torch.empty(max(capacity, 1), dtype=torch.int64, device=bitvec.device)
+    if pos.numel() < capacity:
+        raise ValueError("out holds fewer than `capacity` positions")
+    if num is None:
+        num = torch.empty(1, dtype=torch.int64, device=bitvec.device)
     check(lib().sss_positions(ctx.handle, bitvec.data_ptr(), n, base, pos.data_ptr(), capacity, num.data_ptr(),
                               _stream()), "sss_positions")
     return pos, num
+
+
+def scan_positions(packed: torch.Tensor, n: int, w: int, lo: int, hi: Optional[int] = None, base: int = 0,
+                   capacity: Optional[int] = None, out: Optional[torch.Tensor] = None
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The north star's scan output in one call: bitvector + match count + ascending position list
+    (each position plus `base`) -> (bitvector, positions int64[capacity], count int64[1])."""
+    ctx = Context.current()
+    _check_packed(packed, n, w)
+    hi = lo if hi is None else hi
+    if out is None:
+        out = torch.empty(bitvec_bytes(n), dtype=torch.uint8, device=packed.device)
+    if capacity is None:
+        capacity = n
+    pos = torch.empty(max(capacity, 1), dtype=torch.int64, device=packed.device)
+    count = torch.empty(1, dtype=torch.int64, device=packed.device)
+    check(lib().sss_scan_range_positions(ctx.handle, packed.data_ptr(), n, w, lo & 0xFFFFFFFF, hi & 0xFFFFFFFF,
+                                         out.data_ptr(), count.data_ptr(), base, pos.data_ptr(), capacity, _stream()),
+          "sss_scan_range_positions")
+    return out, pos, count
 
 
 def shared_scan(packed: torch.Tensor, n: int, w: int, lo, hi=None, out: Optional[torch.Tensor] = None,
@@ -304,6 +328,16 @@ def host_shared_scan_linear(packed: Host, n: int, w: int, lo: Sequence[int], hi:
     check(lib().sss_host_shared_scan_linear(ctx.handle, _hptr(packed), n, w, _hptr(lo_a), _hptr(hi_a), K,
                                             tail_granule, _hptr(out), _hptr(counts)), "sss_host_shared_scan_linear")
     return out, counts
+
+
+def host_shared_scan_into(packed: Host, n: int, w: int, lo: np.ndarray, hi: np.ndarray, out: Host, stride: int,
+                          counts: np.ndarray, tail_granule: int = 1) -> None:
+    """sss_host_shared_scan into caller-owned (for full PCIe speed: pinned) buffers: `out` holds K
+    bitvectors `stride` bytes apart, `counts` K uint64."""
+    ctx = Context.current()
+    K = len(lo)
+    check(lib().sss_host_shared_scan(ctx.handle, _hptr(packed), n, w, _hptr(lo), _hptr(hi), K, tail_granule,
+                                     _hptr(out), stride, _hptr(counts)), "sss_host_shared_scan")
 
 
 def pinned_empty(nbytes: int) -> torch.Tensor:

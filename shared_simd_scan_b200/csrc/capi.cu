@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "../../include/sss_b200.h"
@@ -25,6 +26,8 @@ struct Slot {
     size_t in_cap = 0;
     void* d_out = nullptr;
     size_t out_cap = 0;
+    void* h_bounce = nullptr;  // pinned; results whose final host destination is scattered (per-predicate vectors)
+    size_t bounce_cap = 0;
 };
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? SSS_OK : SSS_ERR_CUDA_BASE + (int)e; }
@@ -41,6 +44,8 @@ inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? SSS_OK : SSS_E
         if (_s != SSS_OK) return _s;  \
     } while (0)
 
+#define SSS_LOCK(ctx) std::lock_guard<std::recursive_mutex> _guard((ctx)->mu)
+
 }  // namespace
 
 struct sss_ctx {
@@ -49,8 +54,13 @@ struct sss_ctx {
     uint32_t* d_lo = nullptr;  // SSS_MAX_PREDICATES each, for the host entry points
     uint32_t* d_hi = nullptr;
     unsigned long long* d_counts = nullptr;  // SSS_MAX_PREDICATES + 1
-    void* d_ws = nullptr;                    // positions workspace
+    void* d_ws = nullptr;                    // positions workspace (positions.cu: counters + tile states)
     size_t ws_cap = 0;
+    uint32_t ws_epoch = 0;                   // last epoch the workspace has seen since it was zeroed
+    // Serialises the calls made with this context: the host entry points for their whole (synchronous)
+    // duration, the device entry points while they enqueue.  Calls from several threads are therefore
+    // safe; to run them CONCURRENTLY give every thread its own context (the C++ drop-in layer keeps a pool).
+    std::recursive_mutex mu;
     void* d_index = nullptr;                 // predicate index of the shared scan in flight (predindex.cuh)
     unsigned long long* d_count_slots = nullptr;  // kCountSlots x {accumulator, ticket}, zero between launches
     uint32_t next_count_slot = 0;
@@ -65,6 +75,17 @@ int grow(void** p, size_t* cap, size_t need)
     *p = nullptr;
     *cap = 0;
     SSS_CK(cudaMalloc(p, need));
+    *cap = need;
+    return SSS_OK;
+}
+
+int grow_pinned(void** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return SSS_OK;
+    if (*p) SSS_CK(cudaFreeHost(*p));
+    *p = nullptr;
+    *cap = 0;
+    SSS_CK(cudaMallocHost(p, need));
     *cap = need;
     return SSS_OK;
 }
@@ -146,6 +167,7 @@ const char* sss_error_string(int status)
         case SSS_ERR_UNSUPPORTED: return "unsupported";
         case SSS_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
     }
+    if (status >= SSS_ERR_NCCL_BASE) return "NCCL error (status - 2000 = ncclResult_t)";
     if (status >= SSS_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(status - SSS_ERR_CUDA_BASE));
     return "unknown status";
 }
@@ -196,6 +218,7 @@ int sss_ctx_destroy(sss_ctx* ctx)
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_out) cudaFree(s.d_out);
+        if (s.h_bounce) cudaFreeHost(s.h_bounce);
     }
     if (ctx->d_lo) cudaFree(ctx->d_lo);
     if (ctx->d_hi) cudaFree(ctx->d_hi);
@@ -229,6 +252,7 @@ int sss_pack(sss_ctx* ctx, const uint32_t* d_codes, uint64_t n, int w, void* d_p
 {
     SSS_TRY(check_common(ctx, d_packed, w));
     if (d_codes == nullptr && n != 0) return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     const size_t bytes = sss_packed_bytes(n, w);
     const uint64_t words = bytes / 4;
@@ -241,6 +265,7 @@ int sss_generate_packed(sss_ctx* ctx, void* d_packed, uint64_t n, int w, uint64_
                         void* stream)
 {
     SSS_TRY(check_common(ctx, d_packed, w));
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     const size_t bytes = sss_packed_bytes(n, w);
     const uint64_t words = bytes / 4;
@@ -255,6 +280,7 @@ int sss_unpack(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, int32_t* d
     SSS_TRY(check_common(ctx, d_packed, w));
     if (d_out == nullptr || (reinterpret_cast<uintptr_t>(d_out) & 31)) return SSS_ERR_INVALID_ARG;  // 256-bit stores
     if (n == 0) return SSS_OK;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return cuda_status(launch_unpack(ctx->dev, d_packed, n, w, d_out, static_cast<cudaStream_t>(stream)));
 }
@@ -277,9 +303,26 @@ int sss_scan_range(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32
 {
     SSS_TRY(check_common(ctx, d_packed, w));
     if (d_bitvec == nullptr || (reinterpret_cast<uintptr_t>(d_bitvec) & 15)) return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return scan_range_impl(ctx, d_packed, n, w, lo, hi, d_bitvec, reinterpret_cast<unsigned long long*>(d_count), false,
                            static_cast<cudaStream_t>(stream));
+}
+
+static int positions_impl(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base, uint64_t* d_positions,
+                          uint64_t capacity, uint64_t* d_num, cudaStream_t st)
+{
+    const size_t need = positions_workspace_bytes(n);
+    if (ctx->ws_cap < need || ctx->ws_epoch >= positions_epoch_limit()) {
+        // (re)allocating or re-zeroing the workspace synchronises; callers that time this path warm it up first
+        SSS_CK(cudaStreamSynchronize(st));
+        SSS_TRY(grow(&ctx->d_ws, &ctx->ws_cap, need + need / 4));
+        SSS_CK(cudaMemsetAsync(ctx->d_ws, 0, ctx->ws_cap, st));
+        ctx->ws_epoch = 0;
+    }
+    return cuda_status(launch_positions(ctx->dev, static_cast<const uint32_t*>(d_bitvec), n, base,
+                                        reinterpret_cast<unsigned long long*>(d_positions), capacity,
+                                        reinterpret_cast<unsigned long long*>(d_num), ctx->d_ws, ++ctx->ws_epoch, st));
 }
 
 int sss_positions(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base, uint64_t* d_positions,
@@ -287,17 +330,25 @@ int sss_positions(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base,
 {
     if (ctx == nullptr || d_bitvec == nullptr || (reinterpret_cast<uintptr_t>(d_bitvec) & 3)) return SSS_ERR_INVALID_ARG;
     if (d_positions == nullptr && capacity != 0) return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    return positions_impl(ctx, d_bitvec, n, base, d_positions, capacity, d_num, static_cast<cudaStream_t>(stream));
+}
+
+int sss_scan_range_positions(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32_t lo, uint32_t hi,
+                             void* d_bitvec, uint64_t* d_count, uint64_t base, uint64_t* d_positions,
+                             uint64_t capacity, void* stream)
+{
+    SSS_TRY(check_common(ctx, d_packed, w));
+    if (d_bitvec == nullptr || (reinterpret_cast<uintptr_t>(d_bitvec) & 15)) return SSS_ERR_INVALID_ARG;
+    if (d_positions == nullptr && capacity != 0) return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     auto st = static_cast<cudaStream_t>(stream);
-    const size_t need = positions_workspace_bytes(n);
-    if (ctx->ws_cap < need) {
-        // growing the workspace synchronises; callers that time this path warm it up first
-        SSS_CK(cudaStreamSynchronize(st));
-        SSS_TRY(grow(&ctx->d_ws, &ctx->ws_cap, need + need / 4));
-    }
-    return cuda_status(launch_positions(ctx->dev, static_cast<const uint32_t*>(d_bitvec), n, base,
-                                        reinterpret_cast<unsigned long long*>(d_positions), capacity,
-                                        reinterpret_cast<unsigned long long*>(d_num), ctx->d_ws, st));
+    // the scan writes the bitvector and the count; the position pass reads the bitvector while it is
+    // still (mostly) L2-resident and needs no count of its own
+    SSS_TRY(scan_range_impl(ctx, d_packed, n, w, lo, hi, d_bitvec, reinterpret_cast<unsigned long long*>(d_count), false, st));
+    return positions_impl(ctx, d_bitvec, n, base, d_positions, capacity, nullptr, st);
 }
 
 // One shared scan = build the predicate index, run the scan (which fills the index's interval
@@ -310,6 +361,7 @@ int sss_bitvec_combine(sss_ctx* ctx, int op, const void* d_a, const void* d_b, u
     if (op < SSS_OP_AND || op > SSS_OP_XOR) return SSS_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(d_a) | reinterpret_cast<uintptr_t>(d_b) | reinterpret_cast<uintptr_t>(d_out)) & 15)
         return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     auto st = static_cast<cudaStream_t>(stream);
     if (n == 0) {
@@ -328,6 +380,7 @@ int sss_unpack_at(sss_ctx* ctx, const void* d_packed, int w, const uint64_t* d_p
     SSS_TRY(check_common(ctx, d_packed, w));
     if (num != 0 && (d_positions == nullptr || d_out == nullptr)) return SSS_ERR_INVALID_ARG;
     if (num == 0) return SSS_OK;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return cuda_status(launch_unpack_at(ctx->dev, d_packed, w, reinterpret_cast<const unsigned long long*>(d_positions),
                                         num, d_out, static_cast<cudaStream_t>(stream)));
@@ -339,6 +392,7 @@ int sss_calibrate(sss_ctx* ctx, int mode, const void* d_a, void* d_b, uint64_t b
     if (mode != SSS_CALIB_WRITE && (d_a == nullptr || (reinterpret_cast<uintptr_t>(d_a) & 15))) return SSS_ERR_INVALID_ARG;
     if (mode != SSS_CALIB_READ && (d_b == nullptr || (reinterpret_cast<uintptr_t>(d_b) & 15))) return SSS_ERR_INVALID_ARG;
     if (mode == SSS_CALIB_MIX && (ratio == 0 || ratio > 64)) return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return cuda_status(launch_calibrate(ctx->dev, mode, d_a, d_b, bytes, ratio, ctx->d_counts + SSS_MAX_PREDICATES,
                                         static_cast<cudaStream_t>(stream)));
@@ -405,6 +459,7 @@ int sss_shared_scan(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, const
     if (d_lo == nullptr || d_hi == nullptr || d_bitvecs == nullptr) return SSS_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(d_bitvecs) & 3) || (stride_bytes & 3) || stride_bytes < 4 * ((n + 31) / 32))
         return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return shared_impl(ctx, false, d_packed, n, w, d_lo, d_hi, K, d_bitvecs, stride_bytes,
                        reinterpret_cast<unsigned long long*>(d_counts), static_cast<cudaStream_t>(stream));
@@ -416,6 +471,7 @@ int sss_shared_scan_linear(sss_ctx* ctx, const void* d_packed, uint64_t n, int w
     SSS_TRY(check_common(ctx, d_packed, w));
     SSS_TRY(check_k(K));
     if (d_lo == nullptr || d_hi == nullptr || d_out == nullptr) return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return shared_impl(ctx, true, d_packed, n, w, d_lo, d_hi, K, d_out, 0,
                        reinterpret_cast<unsigned long long*>(d_counts), static_cast<cudaStream_t>(stream));
@@ -431,6 +487,7 @@ int sss_shared_scan_linear(sss_ctx* ctx, const void* d_packed, uint64_t n, int w
 int sss_host_unpack(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, int32_t* h_out)
 {
     if (ctx == nullptr || h_packed == nullptr || h_out == nullptr || w < 1 || w > 32) return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     const uint64_t C = chunk_codes(w / 8.0, 4.0);
     int slot = 0;
@@ -454,6 +511,7 @@ int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, u
 {
     if (ctx == nullptr || h_packed == nullptr || h_bitvec == nullptr || w < 1 || w > 32) return SSS_ERR_INVALID_ARG;
     if (!tail_mode_ok(tail_granule)) return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     const uint64_t n_eval = eval_codes_for(n, w, tail_granule);
     const uint64_t out_total = out_bytes_for(n, w, tail_granule);
@@ -490,6 +548,7 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
     if (w < 1 || w > 32) return SSS_ERR_INVALID_ARG;
     SSS_TRY(check_k(K));
     if (!tail_mode_ok(tail_granule)) return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     const uint64_t n_eval = eval_codes_for(n, w, tail_granule);
     const uint64_t out_total = out_bytes_for(n, w, tail_granule);  // per predicate (bitvectors) / rows (linear)
@@ -502,21 +561,42 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
     const bool single = K == 1;  // see single_predicate_body
     if (!single) SSS_CK(launch_build_pred_index(ctx->d_lo, ctx->d_hi, K, w, ctx->d_index, s0));
     SSS_CK(cudaStreamSynchronize(s0));
+    // Per-predicate destination vectors (h_out_ptrs): one device->host copy per chunk into the slot's
+    // pinned bounce buffer and a host-side scatter of the K pieces once the chunk has landed, instead
+    // of K small copies per chunk (1024 x 8 KB at K = 1024) into pageable memory.
+    struct Pending {
+        bool live = false;
+        uint64_t out_off = 0, piece = 0, stride = 0;
+    } pending[kSlots];
+    const uint64_t chunk_stride = C / 8;  // device-side bitvector stride inside the slot (full chunks)
+    const uint64_t Ca = std::min<uint64_t>(C, round_up_u64(n_eval, 1024));  // codes the staging buffers are sized for
+    auto drain = [&](int sl) -> int {
+        if (!pending[sl].live) return SSS_OK;
+        SSS_CK(cudaStreamSynchronize(ctx->slots[sl].stream));
+        const uint8_t* src = static_cast<const uint8_t*>(ctx->slots[sl].h_bounce);
+        for (int k = 0; k < K; k++)
+            std::memcpy(static_cast<uint8_t*>(h_out_ptrs[k]) + pending[sl].out_off, src + (uint64_t)k * pending[sl].stride,
+                        pending[sl].piece);
+        pending[sl].live = false;
+        return SSS_OK;
+    };
     int slot = 0;
     for (uint64_t first = 0; first < n_eval; first += C, slot = (slot + 1) % kSlots) {
         Slot& s = ctx->slots[slot];
+        if (h_out_ptrs != nullptr) SSS_TRY(drain(slot));  // the slot's previous chunk, before its buffers are reused
         const uint64_t cnt = std::min(C, n_eval - first);
         const uint64_t in_bytes = round_up_u64(((cnt + 31) / 32) * (uint64_t)w * 4, 16);
-        SSS_TRY(grow(&s.d_in, &s.in_cap, round_up_u64(C / 32 * (uint64_t)w * 4, 16) + 16));
-        SSS_TRY(grow(&s.d_out, &s.out_cap, C / 8 * (uint64_t)K));
+        SSS_TRY(grow(&s.d_in, &s.in_cap, round_up_u64(Ca / 32 * (uint64_t)w * 4, 16) + 16));
+        SSS_TRY(grow(&s.d_out, &s.out_cap, (Ca / 8 + 128) * (uint64_t)K));
         const uint8_t* src = static_cast<const uint8_t*>(h_packed) + first * (uint64_t)w / 8;
         SSS_CK(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
-        const uint64_t chunk_stride = C / 8;  // device-side bitvector stride inside the slot
+        // a short (last) chunk packs its bitvectors tightly so that small columns do not move whole-chunk strides
+        const uint64_t dev_stride = std::min(chunk_stride, round_up_u64(4 * ((cnt + 31) / 32), 128));
         if (single)
             SSS_TRY(single_predicate_body(ctx, s.d_in, cnt, w, ctx->d_lo, ctx->d_hi, s.d_out,
                                           h_counts != nullptr ? ctx->d_counts : nullptr, true, s.stream));
         else
-            SSS_TRY(shared_scan_body(ctx, linear, s.d_in, cnt, w, K, s.d_out, chunk_stride,
+            SSS_TRY(shared_scan_body(ctx, linear, s.d_in, cnt, w, K, s.d_out, dev_stride,
                                      h_counts != nullptr ? ctx->d_counts : nullptr, s.stream));
         const uint64_t out_off = first / 8;  // bytes per predicate / rows already produced
         const uint64_t piece = std::min<uint64_t>(4 * ((cnt + 31) / 32), out_total - out_off);
@@ -524,15 +604,17 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
             SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_out) + out_off * (uint64_t)K, s.d_out, piece * (uint64_t)K,
                                    cudaMemcpyDeviceToHost, s.stream));
         } else if (h_out_ptrs != nullptr) {
-            for (int k = 0; k < K; k++)
-                SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_out_ptrs[k]) + out_off,
-                                       static_cast<uint8_t*>(s.d_out) + (uint64_t)k * chunk_stride, piece,
-                                       cudaMemcpyDeviceToHost, s.stream));
+            SSS_TRY(grow_pinned(&s.h_bounce, &s.bounce_cap, (Ca / 8 + 128) * (uint64_t)K));
+            SSS_CK(cudaMemcpyAsync(s.h_bounce, s.d_out, (uint64_t)(K - 1) * dev_stride + piece, cudaMemcpyDeviceToHost,
+                                   s.stream));
+            pending[slot] = Pending{true, out_off, piece, dev_stride};
         } else {
-            SSS_CK(cudaMemcpy2DAsync(static_cast<uint8_t*>(h_out) + out_off, stride_bytes, s.d_out, chunk_stride, piece,
+            SSS_CK(cudaMemcpy2DAsync(static_cast<uint8_t*>(h_out) + out_off, stride_bytes, s.d_out, dev_stride, piece,
                                      (size_t)K, cudaMemcpyDeviceToHost, s.stream));
         }
     }
+    if (h_out_ptrs != nullptr)
+        for (int i = 0; i < kSlots; i++, slot = (slot + 1) % kSlots) SSS_TRY(drain(slot));  // oldest first
     for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
     if (h_counts) {
         if (!single && !counts_directly(linear, K))
@@ -568,10 +650,50 @@ int sss_host_shared_scan_linear(sss_ctx* ctx, const void* h_packed, uint64_t n, 
     return host_shared_impl(ctx, true, h_packed, n, w, h_lo, h_hi, K, tail_granule, h_out, nullptr, 0, h_counts);
 }
 
+// Position list of a HOST bitvector (the result of sss_host_scan_range): the bitvector goes to the
+// device in pieces of 2^25 bits, every piece is expanded there (positions.cu) and its positions come
+// back appended to h_positions -- n/8 bytes up, 8 bytes per match down.  One stream: the kernels share
+// the context's look-back workspace and the running offset needs every piece's count anyway.
+int sss_host_positions(sss_ctx* ctx, const void* h_bitvec, uint64_t n, uint64_t base, uint64_t* h_positions,
+                       uint64_t capacity, uint64_t* h_num)
+{
+    if (ctx == nullptr || (h_bitvec == nullptr && n != 0) || (h_positions == nullptr && capacity != 0))
+        return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
+    SSS_CK(cudaSetDevice(ctx->dev.ordinal));
+    constexpr uint64_t kPiece = 1ull << 25;  // codes per piece: 4 MiB of bitvector, at most 256 MiB of positions
+    Slot& s = ctx->slots[0];
+    uint64_t total = 0;
+    for (uint64_t first = 0; first < n; first += kPiece) {
+        const uint64_t cnt = std::min(kPiece, n - first);
+        const uint64_t room = total < capacity ? capacity - total : 0;
+        const uint64_t cap_piece = std::min(room, cnt);
+        SSS_TRY(grow(&s.d_in, &s.in_cap, kPiece / 8 + 16));
+        SSS_TRY(grow(&s.d_out, &s.out_cap, std::max<uint64_t>(cap_piece, 1) * 8));
+        const uint64_t in_bytes = (cnt + 7) / 8;
+        SSS_CK(cudaMemsetAsync(static_cast<uint8_t*>(s.d_in) + in_bytes / 4 * 4, 0, 8, s.stream));  // ragged last word
+        SSS_CK(cudaMemcpyAsync(s.d_in, static_cast<const uint8_t*>(h_bitvec) + first / 8, in_bytes, cudaMemcpyHostToDevice,
+                               s.stream));
+        SSS_TRY(positions_impl(ctx, s.d_in, cnt, base + first, static_cast<uint64_t*>(s.d_out), cap_piece,
+                               reinterpret_cast<uint64_t*>(ctx->d_counts), s.stream));
+        unsigned long long got = 0;
+        SSS_CK(cudaMemcpyAsync(&got, ctx->d_counts, sizeof(got), cudaMemcpyDeviceToHost, s.stream));
+        SSS_CK(cudaStreamSynchronize(s.stream));
+        const uint64_t take = std::min<uint64_t>(got, cap_piece);
+        if (take)
+            SSS_CK(cudaMemcpyAsync(h_positions + total, s.d_out, take * 8, cudaMemcpyDeviceToHost, s.stream));
+        total += got;
+    }
+    SSS_CK(cudaStreamSynchronize(s.stream));
+    if (h_num) *h_num = total;
+    return SSS_OK;
+}
+
 int sss_host_pack(sss_ctx* ctx, const uint32_t* h_codes, uint64_t n, int w, void* h_packed)
 {
     if (ctx == nullptr || h_packed == nullptr || (h_codes == nullptr && n != 0) || w < 1 || w > 32)
         return SSS_ERR_INVALID_ARG;
+    SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     const size_t total = sss_packed_bytes(n, w);
     std::memset(h_packed, 0, total);  // padding (and everything, for n == 0)

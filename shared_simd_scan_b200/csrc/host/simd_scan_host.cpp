@@ -8,28 +8,115 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <condition_variable>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "sss_b200.h"
 
 namespace {
 
-sss_ctx* context()
+// The reference's functions are stateless and may be called from any number of threads at once
+// (src/simd_scan.cpp:103-158; its own shared_scan_128_threaded calls scan_128 from an OpenMP team,
+// src/simd_scan_shared.cpp:25-32).  A GPU context is not stateless -- streams, staging buffers, the
+// predicate index of the shared scan in flight -- so the drop-in keeps a POOL of contexts: every call
+// leases one for its duration, concurrent callers get different contexts (created on demand, up to
+// SSS_HOST_CONTEXTS, default 8; further callers wait for a free one).  SSS_DEVICE picks the GPU;
+// SSS_DEVICES=0,1,... spreads the pool's contexts round-robin over several GPUs.
+class ContextPool {
+public:
+    sss_ctx* acquire()
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            if (!free_.empty()) {
+                sss_ctx* c = free_.back();
+                free_.pop_back();
+                return c;
+            }
+            if (created_ < limit()) {
+                const int ordinal = created_++;
+                lk.unlock();
+                sss_ctx* c = nullptr;
+                const int status = sss_ctx_create(device_for(ordinal), &c);
+                if (status != SSS_OK) {
+                    lk.lock();
+                    created_--;
+                    cv_.notify_one();
+                    throw std::runtime_error(std::string("shared_simd_scan_b200: cannot create a GPU context: ") +
+                                             sss_error_string(status));
+                }
+                return c;
+            }
+            cv_.wait(lk);
+        }
+    }
+    void release(sss_ctx* c)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            free_.push_back(c);
+        }
+        cv_.notify_one();
+    }
+
+private:
+    static int limit()
+    {
+        static const int v = [] {
+            const char* e = std::getenv("SSS_HOST_CONTEXTS");
+            const int n = e ? std::atoi(e) : 8;
+            return n < 1 ? 1 : (n > 64 ? 64 : n);
+        }();
+        return v;
+    }
+    static int device_for(int ordinal)
+    {
+        static const std::vector<int> devices = [] {
+            std::vector<int> d;
+            if (const char* list = std::getenv("SSS_DEVICES")) {
+                for (const char* p = list; *p;) {
+                    char* end = nullptr;
+                    const long v = std::strtol(p, &end, 10);
+                    if (end == p) break;
+                    d.push_back((int)v);
+                    p = (*end == ',') ? end + 1 : end;
+                }
+            }
+            if (d.empty()) {
+                const char* one = std::getenv("SSS_DEVICE");
+                d.push_back(one ? std::atoi(one) : 0);
+            }
+            return d;
+        }();
+        return devices[(size_t)ordinal % devices.size()];
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<sss_ctx*> free_;  // (contexts live until process exit, like the CUDA primary context)
+    int created_ = 0;
+};
+
+ContextPool& pool()
 {
-    static sss_ctx* ctx = nullptr;
-    static std::once_flag once;
-    static int status = SSS_OK;
-    std::call_once(once, [] {
-        const char* dev = std::getenv("SSS_DEVICE");
-        status = sss_ctx_create(dev ? std::atoi(dev) : 0, &ctx);
-    });
-    if (status != SSS_OK)
-        throw std::runtime_error(std::string("shared_simd_scan_b200: cannot create a GPU context: ") +
-                                 sss_error_string(status));
-    return ctx;
+    static ContextPool* p = new ContextPool();  // never destroyed: no CUDA calls during static destruction
+    return *p;
 }
+
+// a context for the duration of one call
+class Lease {
+public:
+    Lease() : ctx_(pool().acquire()) {}
+    ~Lease() { pool().release(ctx_); }
+    Lease(const Lease&) = delete;
+    Lease& operator=(const Lease&) = delete;
+    operator sss_ctx*() const { return ctx_; }
+
+private:
+    sss_ctx* ctx_;
+};
 
 void must(int status, const char* what)
 {
@@ -88,7 +175,8 @@ void shared_impl(int w, int tail, const std::vector<sss_host::Range>& ranges, co
     }
     std::vector<uint64_t> local;
     if (counts) counts->assign(ranges.size(), 0);
-    must(sss_host_shared_scan_ptrs(context(), input, n, w, lo.data(), hi.data(), (int)ranges.size(), tail, ptrs.data(),
+    Lease ctx;
+    must(sss_host_shared_scan_ptrs(ctx, input, n, w, lo.data(), hi.data(), (int)ranges.size(), tail, ptrs.data(),
                                    counts ? counts->data() : nullptr),
          "shared scan");
 }
@@ -101,7 +189,8 @@ void linear_impl(int w, const std::vector<sss_host::Range>& ranges, const void* 
     split(ranges, lo, hi);
     require_bytes(output.size(), sss_tail_out_bytes(n, w, SSS_TAIL_8) * ranges.size(), "linear shared scan");
     if (counts) counts->assign(ranges.size(), 0);
-    must(sss_host_shared_scan_linear(context(), input, n, w, lo.data(), hi.data(), (int)ranges.size(), SSS_TAIL_8,
+    Lease ctx;
+    must(sss_host_shared_scan_linear(ctx, input, n, w, lo.data(), hi.data(), (int)ranges.size(), SSS_TAIL_8,
                                      output.data(), counts ? counts->data() : nullptr),
          "linear shared scan");
 }
@@ -114,7 +203,8 @@ std::unique_ptr<uint64_t[]> compress(int w, const std::vector<uint32_t>& input)
 {
     const size_t bytes = sss_packed_bytes(input.size(), w);
     auto buffer = std::make_unique<uint64_t[]>((bytes + 7) / 8);  // zero-initialised, like the reference's
-    must(sss_host_pack(context(), input.data(), input.size(), w, buffer.get()), "compress");
+    Lease ctx;
+    must(sss_host_pack(ctx, input.data(), input.size(), w, buffer.get()), "compress");
     return buffer;
 }
 
@@ -125,7 +215,8 @@ std::unique_ptr<uint64_t[]> compress(int w, const std::vector<uint16_t>& input)
 
 void decompress(int w, const void* input, size_t input_size, int* output)
 {
-    must(sss_host_unpack(context(), input, input_size, w, output), "decompress");
+    Lease ctx;
+    must(sss_host_unpack(ctx, input, input_size, w, output), "decompress");
 }
 
 int scan(int w, Tail tail, int predicate_key, const void* input, size_t input_size, std::vector<uint8_t>& output)
@@ -133,7 +224,8 @@ int scan(int w, Tail tail, int predicate_key, const void* input, size_t input_si
     const Range r = key_range(w, predicate_key);
     require_bytes(output.size(), sss_tail_out_bytes(input_size, w, tail), "scan");
     uint64_t hits = 0;
-    must(sss_host_scan_range(context(), input, input_size, w, r.lo, r.hi, tail, output.data(), &hits), "scan");
+    Lease ctx;
+    must(sss_host_scan_range(ctx, input, input_size, w, r.lo, r.hi, tail, output.data(), &hits), "scan");
     return static_cast<int>(hits);  // the reference's return type (overflows past 2^31 matches)
 }
 
@@ -154,16 +246,16 @@ uint64_t scan_range(int w, Range r, const void* input, size_t input_size, std::v
 {
     require_bytes(output.size(), sss_tail_out_bytes(input_size, w, SSS_TAIL_EXACT), "scan_range");
     uint64_t hits = 0;
-    must(sss_host_scan_range(context(), input, input_size, w, r.lo, r.hi, SSS_TAIL_EXACT, output.data(), &hits),
+    Lease ctx;
+    must(sss_host_scan_range(ctx, input, input_size, w, r.lo, r.hi, SSS_TAIL_EXACT, output.data(), &hits),
          "scan_range");
     if (positions) {
-        // ascending positions of the set bits (get_bit order, reference src/util.cpp:51-58); the
-        // bitvector is already on the host, so this is plain bit iteration, not a second scan
-        positions->clear();
-        positions->reserve(hits);
-        for (size_t byte = 0; byte < (input_size + 7) / 8; byte++)
-            for (uint8_t b = output[byte]; b; b &= b - 1)
-                positions->push_back(byte * 8 + static_cast<unsigned>(__builtin_ctz(b)));
+        // ascending positions of the set bits (get_bit order, reference src/util.cpp:51-58), expanded on
+        // the GPU from the bitvector (n/8 bytes up, 8 bytes per match down)
+        positions->assign(hits, 0);
+        uint64_t num = 0;
+        must(sss_host_positions(ctx, output.data(), input_size, 0, positions->data(), hits, &num), "scan_range positions");
+        if (num != hits) throw std::runtime_error("shared_simd_scan_b200: scan_range: position count != match count");
     }
     return hits;
 }

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <sstream>
 #include <iostream>
+#include <thread>
 
 static int failures = 0;
 #define REQUIRE(cond)                                                          \
@@ -186,6 +187,58 @@ static void test_additive_api()
     REQUIRE(outs[0] == out);
 }
 
+static void test_concurrent_callers()
+{
+    // The reference's functions are stateless (src/simd_scan.cpp:103-158) and its own threaded variant
+    // calls scan_128 from an OpenMP team (src/simd_scan_shared.cpp:25-32): 8 threads call scan_128 and
+    // shared_scan_128_standard at the same time, each on its OWN column, and every result must equal
+    // the single-threaded one.
+    constexpr int kThreads = 8;
+    const uint32_t mask = BITS_NEEDED >= 16 ? 0xFFFFu : ((1u << BITS_NEEDED) - 1u);
+    const size_t n = 200003;
+    std::vector<std::vector<uint16_t>> columns(kThreads, std::vector<uint16_t>(n));
+    for (int t = 0; t < kThreads; t++)
+        for (size_t i = 0; i < n; i++) columns[t][i] = (uint16_t)(((i + 1) * 2654435761u * (t + 3)) >> 7) & mask;
+    std::vector<std::unique_ptr<uint64_t[]>> packed(kThreads);
+    for (int t = 0; t < kThreads; t++) packed[t] = compress_9bit_input(columns[t]);
+    const std::vector<int> keys = {1, 2, 3, (int)mask, 0, 77 & (int)mask};
+    struct Result {
+        int hits = 0;
+        std::vector<uint8_t> scan;
+        std::vector<std::vector<uint8_t>> shared;
+    };
+    auto run = [&](int t, Result& r) {
+        r.scan.assign(scan_output_buffer_size(n), 0);
+        r.hits = scan_128(columns[t][5], (__m128i*)packed[t].get(), n, r.scan);
+        r.shared.assign(keys.size(), std::vector<uint8_t>(scan_output_buffer_size(n), 0));
+        shared_scan_128_standard(keys, (__m128i*)packed[t].get(), n, r.shared);
+    };
+    std::vector<Result> serial(kThreads), parallel(kThreads);
+    for (int t = 0; t < kThreads; t++) run(t, serial[t]);
+    for (int round = 0; round < 3; round++) {
+        std::vector<std::thread> team;
+        for (int t = 0; t < kThreads; t++) team.emplace_back([&, t] { run(t, parallel[t]); });
+        for (auto& th : team) th.join();
+        for (int t = 0; t < kThreads; t++) {
+            REQUIRE(parallel[t].hits == serial[t].hits);
+            REQUIRE(parallel[t].scan == serial[t].scan);
+            REQUIRE(parallel[t].shared == serial[t].shared);
+        }
+    }
+    // and the serial results are right
+    for (int t = 0; t < kThreads; t++) {
+        int expect = 0;
+        bool bits = true;
+        for (size_t i = 0; i < n; i++) {
+            const bool hit = columns[t][i] == columns[t][5];
+            expect += hit;
+            bits &= get_bit(serial[t].scan, i) == hit;
+        }
+        REQUIRE(serial[t].hits == expect);
+        REQUIRE(bits);
+    }
+}
+
 int main()
 {
     try {
@@ -194,6 +247,7 @@ int main()
         test_shared_scan();
         test_simple_shared_scan();
         test_additive_api();
+        test_concurrent_callers();
     } catch (std::exception const& e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;

@@ -6,6 +6,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -27,6 +29,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "codes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert len(lines[0]) < 6000, "the driver parses ONE compact line (round 1's 27 KB line came back unparsed)"
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():
@@ -45,3 +48,29 @@ def test_product_arm_refuses_to_run_without_a_gpu():
     assert r.returncode != 0
     assert r.stdout.strip() == ""          # no JSON line from a CPU fallback
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+@pytest.mark.gpu
+def test_product_arm_prints_one_compact_parsable_line(tmp_path):
+    """The product arm on a GPU (small column so that it runs in seconds): ONE JSON line, < 6 KB, the same
+    keys the driver reads at every N, the full tables in the side file it names."""
+    extras = tmp_path / "extras.json"
+    r = _run("--steps", "2", "--warmup", "1", "--logn", "22", "--e2e-steps", "1", "--cpu-logn", "18", "--cfg5-logn", "22",
+             "--no-sweep", "--extras-file", str(extras))
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[-2000:]
+    assert len(lines[0]) < 6000
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline",
+                "summary", "per_width_frac", "extras_file"):
+        assert key in d, key
+    assert d["value"] > 0 and d["gpu_launches"] == 2 * 32 and len(d["per_width_frac"]) == 32
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["roofline"]["bound"] == "hbm" and d["roofline"]["frac"] > 0
+    assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["summary"]["cfg5_shared_k64_w23"]["gcodes_per_s"] > 0
+    side = json.loads(extras.read_text())
+    for key in ("per_width", "shared", "unpack", "pack", "positions", "calibration", "cfg1"):
+        assert key in side, key

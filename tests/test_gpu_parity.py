@@ -518,3 +518,87 @@ def test_calibration_kernels_move_the_bytes(sss):
     sss.calibrate("mix", a, b, nbytes, 4)
     torch.cuda.synchronize()
     assert not b[nbytes // 4 + 64:].any()          # nothing beyond bytes/ratio is written
+
+
+# ---- the benchmarked grid, cell by cell ---------------------------------------------------------------
+# bench.py's shared_sweep publishes a number for every (op, w, K) with w = 1..32 and K in {1, 8, 64, 1024}.
+# Every width is its own template<int W> instantiation with width-class-specific loads and rotations, and
+# every K class takes a different kernel (scan kernel / narrow + few-predicate kernels / thread-per-block /
+# predicate groups / warp-per-block), so every cell gets its own oracle comparison: uniform ranges drawn
+# the way the bench draws them, plus one equality predicate that certainly hits, one empty range, one
+# full-domain range; ragged n; both layouts; counts.
+@pytest.mark.parametrize("K", [1, 8, 64, 1024])
+@pytest.mark.parametrize("w", ALL_W)
+def test_benchmarked_grid_matches_oracle(sss, w, K):
+    m = (1 << w) - 1
+    rng = np.random.default_rng(50_000 + 100 * w + K)
+    n = 8192 * 2 + 77
+    codes, packed = column(n, w, seed=700 + w)
+    lo = rng.integers(0, m + 1, size=K, dtype=np.uint64)
+    hi = np.minimum(lo + rng.integers(0, max(2, 2 * (m + 1) // K), size=K, dtype=np.uint64), m)
+    if K == 1:
+        lo[0] = hi[0] = int(codes[n // 2])                 # the reference's own semantics: equality
+    else:
+        lo[1] = hi[1] = int(codes[n // 2])                 # an equality predicate that certainly hits
+        lo[K // 2], hi[K // 2] = min(7, m), min(3, m - 1) if m > 0 else 0   # an empty range (lo > hi)
+        if lo[K // 2] <= hi[K // 2]:
+            lo[K // 2], hi[K // 2] = 1, 0
+        lo[K - 1], hi[K - 1] = 0, m                        # everything
+    d_packed = dev(packed)
+    nb = (n + 7) // 8
+    exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
+    bv, cnt = sss.shared_scan(d_packed, n, w, lo, hi)
+    got = host(bv)
+    assert (got[:, :nb] == exp).all(), (w, K)
+    assert not got[:, nb: 4 * ((n + 31) // 32)].any(), "bits >= n must be zero"
+    assert (host(cnt).astype(np.uint64) == ecnt).all(), (w, K)
+    lexp, lcnt = B.shared_scan_linear(packed, n, w, lo, hi, granule=1)
+    lin, cnt2 = sss.shared_scan_linear(d_packed, n, w, lo, hi)
+    lgot = host(lin)
+    assert (lgot[:nb] == lexp).all(), (w, K)
+    assert not lgot[nb:].any()
+    assert (host(cnt2).astype(np.uint64) == lcnt).all(), (w, K)
+
+
+@pytest.mark.parametrize("w", [2, 9, 17, 32])
+def test_scan_positions_one_call(sss, w):
+    """sss_scan_range_positions: bitvector + count + ascending positions (+ base) from one call."""
+    m = (1 << w) - 1
+    for n in [1, 77, 65_536 + 3, 1_000_003]:
+        codes, packed = column(n, w, seed=900 + w)
+        for lo, hi in [(0, m // 3), (int(codes[0]), int(codes[0])), (1, 0), (0, m)]:
+            bv, pos, cnt = sss.scan_positions(dev(packed), n, w, lo, hi, base=1 << 40)
+            exp, ecnt = B.scan_range(packed, n, w, lo, hi, granule=1)
+            assert (host(bv)[: len(exp)] == exp).all() and int(cnt.item()) == ecnt
+            epos = B.positions(exp, n, base=1 << 40)
+            assert (host(pos)[:ecnt].astype(np.uint64) == epos).all(), (w, n, lo, hi)
+
+
+def test_positions_many_tiles_and_reuse(sss):
+    """The single-pass position list across thousands of look-back tiles, dense and sparse, called
+    repeatedly on one context (epoch-tagged tile states: no clearing between launches) and with
+    different sizes back to back."""
+    w = 7
+    m = (1 << w) - 1
+    n_big = (1 << 27) + 12_345
+    d_packed = sss.generate_packed(n_big, w, seed=31)
+    for rep, (n, lo, hi) in enumerate([(n_big, 0, m // 2), (1 << 20, 0, 0), (n_big, 5, 5), (3_000_001, 0, m),
+                                        (n_big, 0, m // 2)]):
+        bv, cnt = sss.scan(d_packed, n, w, lo, hi)
+        pos, num = sss.positions(bv, n, base=rep, capacity=int(cnt.item()))
+        k = int(num.item())
+        assert k == int(cnt.item())
+        p = pos[:k]
+        if k > 1:
+            assert bool((p[1:] > p[:-1]).all()), "positions must be strictly ascending"
+        # every listed position has its bit set, and there are exactly popcount of them
+        idx = p - rep
+        bits = (bv[(idx >> 3)].to(torch.int64) >> (idx & 7)) & 1
+        assert bool(bits.all())
+    # a window against the oracle
+    n = 1 << 18
+    packed = host(d_packed[: n * w // 8 + 300])
+    exp, _ = B.scan_range(packed, n, w, 0, m // 2, granule=1)
+    bv, cnt = sss.scan(d_packed, n, w, 0, m // 2)
+    pos, num = sss.positions(bv, n)
+    assert (host(pos)[: int(num.item())].astype(np.uint64) == B.positions(exp, n)).all()

@@ -95,6 +95,10 @@ def main(argv):
         codes, packed = column(n, lambda i: i % K % 512)
         keys = list(range(K))
         print("## shared scan benchmarks ##")
+        print("# B200 (sm_100a) kernels of shared_simd_scan_b200; the variant labels below are the reference's, kept so")
+        print("# that scripts/prepare_shared_scan_results.py / plot_shared_scan_results.py work unchanged:")
+        print("#   'sse 128, sequential (unrolled)' = K single-predicate GPU scans, 'sse 128, standard' = the shared-scan")
+        print("#   kernel (K bitvectors), 'sse 128, linear, standard' = the linear-layout shared-scan kernel")
         print(f"compressed input: {n} ({data_size} bytes)")
         print(f"predicate key count: {K}")
         stride = (api.bitvec_bytes(n) + 15) // 16 * 16
