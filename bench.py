@@ -143,7 +143,12 @@ def _cpu_column(w, logn, seed=42):
         rng = np.random.default_rng(seed + w)
         packed = np.zeros(B.compressed_buffer_size(w, n), dtype=np.uint8)
         payload = n * w // 8
-        packed[:payload] = np.frombuffer(rng.bytes(payload), dtype=np.uint8)
+        # numpy draws ~1 GB/s: columns beyond 64 MiB repeat a 64 MiB random block (the scan's speed does
+        # not depend on the values; the sample only has to be too large for the caches)
+        block = np.frombuffer(rng.bytes(min(payload, 64 << 20)), dtype=np.uint8)
+        for off in range(0, payload, len(block)):
+            m = min(len(block), payload - off)
+            packed[off:off + m] = block[:m]
         _cpu_columns[key] = packed
     return _cpu_columns[key]
 
@@ -425,11 +430,12 @@ def measure_e2e_scan(D, api, columns, n, e2e_steps):
         for w in WIDTHS:
             nb = api.packed_bytes(n, w)
             h_in[:nb].copy_(columns[w][:nb])  # refill the host column (untimed)
-            torch.cuda.synchronize()
+            D.barrier()  # every rank has refilled: no rank's untimed D2H competes with another's timed H2D
             lo, hi = predicate(w)
             t0 = time.perf_counter()
             _, c = api.host_scan(h_in, n, w, lo, hi, tail_granule=1, out=h_out)
             sec += time.perf_counter() - t0
+            D.barrier()
             h2d += (n // 32) * w * 4
             d2h += n // 8 + 8
             if s == e2e_steps:
@@ -748,6 +754,41 @@ def measure_cfg1(torch, api, peak):
             "note": "25 MB working set: L2-resident after the first launch, so the fraction can exceed the HBM roofline"}
 
 
+def measure_e2e_pageable(torch, api, columns, n):
+    """What the C++ drop-in's callers really hand in: PAGEABLE host memory (make_unique / std::vector,
+    src/simd_scan.hpp:46-120).  The host entry points stage such buffers through pinned bounce buffers
+    with a few copy threads (capi.cu HostPipe); numbers for the scan (input-bound) and the decompression
+    (output-bound) at 17 bit, next to the same calls on pinned buffers."""
+    import numpy as np
+    w = 17
+    rows = []
+    nb = api.packed_bytes(n, w)
+    pageable_in = np.empty(nb, dtype=np.uint8)
+    pinned_in = api.pinned_empty(nb)
+    pinned_in.copy_(columns[w][:nb])
+    pageable_in[:] = pinned_in.numpy()
+    m = (1 << w) - 1
+    n2 = min(n, 1 << 28)
+    for kind, buf in (("pageable", pageable_in), ("pinned", pinned_in)):
+        out = np.zeros(api.bitvec_bytes(n), dtype=np.uint8) if kind == "pageable" else api.pinned_empty(api.bitvec_bytes(n))
+        api.host_scan(buf, n, w, m // 4, m // 2, tail_granule=1, out=out)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            api.host_scan(buf, n, w, m // 4, m // 2, tail_granule=1, out=out)
+        sec = (time.perf_counter() - t0) / 3
+        rows.append({"op": "scan", "w": w, "host_memory": kind, "gcodes_per_s": round(n / sec / 1e9, 2),
+                     "h2d_gb_per_s": round(n * w / 8 / sec / 1e9, 1)})
+        dec = np.empty(n2, dtype=np.int32) if kind == "pageable" else api.pinned_empty(n2 * 4).view(torch.int32)
+        api.host_decompress(buf, n2, w, out=dec)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            api.host_decompress(buf, n2, w, out=dec)
+        sec = (time.perf_counter() - t0) / 3
+        rows.append({"op": "decompress", "w": w, "host_memory": kind, "gcodes_per_s": round(n2 / sec / 1e9, 2),
+                     "d2h_gb_per_s": round(n2 * 4 / sec / 1e9, 1)})
+    return rows
+
+
 def extras(args, api, columns, n, peak):
     """Per-K shared-scan numbers and the decompression sweep (BASELINE.json configs 2-4), measured
     after the timed steps with the same event discipline (3 warm-ups, mean of 5)."""
@@ -767,6 +808,7 @@ def extras(args, api, columns, n, peak):
 
     out = {"shared": [], "unpack": [], "pack": [], "positions": [], "calibration": calibration(api, timed, peak),
            "cfg1": measure_cfg1(torch, api, peak)}
+    out["e2e_pageable"] = measure_e2e_pageable(torch, api, columns, n)
     if not args.no_sweep:
         out["shared_sweep"] = shared_sweep(args, api, columns, n, peak)
     for kind, w, K, logn in (("shared", 17, 8, 30), ("shared", 17, 64, 30), ("shared", 23, 64, 30),
@@ -933,8 +975,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--logn", type=int, default=30, help="log2 codes per width per GPU (BASELINE: 30)")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-logn", type=int, default=27, help="cpu_baseline sample: log2 codes per width")
-    ap.add_argument("--ref-logn", type=int, default=26, help="--impl reference sample: log2 codes per width per step")
+    ap.add_argument("--cpu-logn", type=int, default=28, help="cpu_baseline sample: log2 codes per width")
+    ap.add_argument("--ref-logn", type=int, default=28, help="--impl reference sample: log2 codes per width per step")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "cfg5"],
                     help="sweep = the contract line; cfg5 = the sharded shared scan (K=64, 23 bit) alone")
     ap.add_argument("--cfg5-logn", type=int, default=31, help="cfg5: log2 codes per GPU")

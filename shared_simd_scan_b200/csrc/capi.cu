@@ -8,6 +8,8 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "../../include/sss_b200.h"
 #include "kernels.h"
@@ -26,8 +28,10 @@ struct Slot {
     size_t in_cap = 0;
     void* d_out = nullptr;
     size_t out_cap = 0;
-    void* h_bounce = nullptr;  // pinned; results whose final host destination is scattered (per-predicate vectors)
+    void* h_bounce = nullptr;  // pinned; results on their way to pageable or scattered host destinations
     size_t bounce_cap = 0;
+    void* h_in_bounce = nullptr;  // pinned; pageable input on its way to the device
+    size_t in_bounce_cap = 0;
 };
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? SSS_OK : SSS_ERR_CUDA_BASE + (int)e; }
@@ -153,6 +157,118 @@ uint64_t chunk_codes(double in_bytes_per_code, double out_bytes_per_code)
     return c < 1024 ? 1024 : c;
 }
 
+
+// ---- pageable host memory -----------------------------------------------------------------------
+//
+// The reference's callers hand in make_unique / std::vector memory (src/simd_scan.hpp:46-120), i.e.
+// PAGEABLE buffers.  Measured on the B200 box (profiles/r02_h2d_probe.txt): cudaMemcpy from pageable
+// memory 10 GB/s (to: 18 GB/s), pinned 55 GB/s, cudaHostRegister on the fly 7 GB/s to pin plus a slower
+// unregister -- it never pays.  What pays is staging through the slots' pinned bounce buffers with a few
+// host threads doing the memcpy (8 threads: 34 GB/s end to end, overlapped with the DMA of the
+// neighbouring chunks).
+int copy_threads()
+{
+    static const int v = [] {
+        const char* e = std::getenv("SSS_COPY_THREADS");
+        int t = e ? std::atoi(e) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        return t < 1 ? 1 : (t > 32 ? 32 : t);
+    }();
+    return v;
+}
+
+void par_memcpy(void* dst, const void* src, size_t bytes)
+{
+    const int T = copy_threads();
+    if (T <= 1 || bytes < (4u << 20)) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t per = ((bytes + T - 1) / T + 4095) & ~(size_t)4095;
+    std::vector<std::thread> team;
+    for (int t = 1; t < T; t++) {
+        const size_t off = per * t;
+        if (off >= bytes) break;
+        team.emplace_back([=] {
+            std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(per, bytes - off));
+        });
+    }
+    std::memcpy(dst, src, std::min(per, bytes));
+    for (auto& t : team) t.join();
+}
+
+bool is_pageable(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// The staging pipeline of one host-buffer call: chunk c uses slot c % kSlots (own stream, own device
+// buffers, own bounce buffers).  acquire() makes a slot reusable: it waits for the slot's stream and
+// then hands the slot's finished results to their pageable / scattered destinations, so the host
+// copies of chunk c overlap the DMA and kernels of chunks c+1 and c+2.
+class HostPipe {
+public:
+    struct Piece {
+        void* dst;
+        size_t src_off, bytes;
+    };
+    HostPipe(sss_ctx* ctx, bool in_pageable, bool out_staged) : ctx_(ctx), in_pageable_(in_pageable), out_staged_(out_staged) {}
+    bool out_staged() const { return out_staged_; }
+
+    int acquire(int sl)
+    {
+        Slot& s = ctx_->slots[sl];
+        if (!busy_[sl]) return SSS_OK;
+        // stream order alone protects the device buffers; the host has to wait only before it touches a
+        // bounce buffer again (pageable input) or owes the slot's results to somebody
+        if (!in_pageable_ && owed_[sl].empty()) return SSS_OK;
+        SSS_CK(cudaStreamSynchronize(s.stream));
+        for (const Piece& p : owed_[sl])
+            par_memcpy(p.dst, static_cast<const uint8_t*>(s.h_bounce) + p.src_off, p.bytes);
+        owed_[sl].clear();
+        busy_[sl] = false;
+        return SSS_OK;
+    }
+    // host -> slot.d_in (after acquire)
+    int copy_in(int sl, const void* src, size_t bytes, size_t cap_hint)
+    {
+        Slot& s = ctx_->slots[sl];
+        busy_[sl] = true;
+        if (!in_pageable_) return cuda_status(cudaMemcpyAsync(s.d_in, src, bytes, cudaMemcpyHostToDevice, s.stream));
+        SSS_TRY(grow_pinned(&s.h_in_bounce, &s.in_bounce_cap, std::max(bytes, cap_hint)));
+        par_memcpy(s.h_in_bounce, src, bytes);
+        return cuda_status(cudaMemcpyAsync(s.d_in, s.h_in_bounce, bytes, cudaMemcpyHostToDevice, s.stream));
+    }
+    // staged results: slot.d_out[0, extent) -> the slot's bounce buffer now, `pieces` of it -> their
+    // destinations when the slot is next acquired (or at finish)
+    int copy_out_staged(int sl, size_t extent, size_t cap_hint, std::vector<Piece>&& pieces)
+    {
+        Slot& s = ctx_->slots[sl];
+        busy_[sl] = true;
+        SSS_TRY(grow_pinned(&s.h_bounce, &s.bounce_cap, std::max(extent, cap_hint)));
+        SSS_CK(cudaMemcpyAsync(s.h_bounce, s.d_out, extent, cudaMemcpyDeviceToHost, s.stream));
+        owed_[sl] = std::move(pieces);
+        return SSS_OK;
+    }
+    // oldest chunk first
+    int finish(int next_slot)
+    {
+        for (int i = 0; i < kSlots; i++) SSS_TRY(acquire((next_slot + i) % kSlots));
+        for (auto& s : ctx_->slots) SSS_CK(cudaStreamSynchronize(s.stream));
+        return SSS_OK;
+    }
+
+private:
+    sss_ctx* ctx_;
+    bool in_pageable_, out_staged_;
+    bool busy_[kSlots] = {};
+    std::vector<Piece> owed_[kSlots];
+};
+
 }  // namespace
 
 extern "C" {
@@ -219,6 +335,7 @@ int sss_ctx_destroy(sss_ctx* ctx)
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_out) cudaFree(s.d_out);
         if (s.h_bounce) cudaFreeHost(s.h_bounce);
+        if (s.h_in_bounce) cudaFreeHost(s.h_in_bounce);
     }
     if (ctx->d_lo) cudaFree(ctx->d_lo);
     if (ctx->d_hi) cudaFree(ctx->d_hi);
@@ -490,20 +607,26 @@ int sss_host_unpack(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, int32
     SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     const uint64_t C = chunk_codes(w / 8.0, 4.0);
+    const uint64_t Ca = std::min<uint64_t>(C, round_up_u64(n, 1024));
+    const size_t in_cap = round_up_u64(packed_payload_bytes(Ca, w), 16) + 16;
+    HostPipe pipe(ctx, is_pageable(h_packed), is_pageable(h_out));
     int slot = 0;
     for (uint64_t first = 0; first < n; first += C, slot = (slot + 1) % kSlots) {
         Slot& s = ctx->slots[slot];
+        SSS_TRY(pipe.acquire(slot));
         const uint64_t cnt = std::min(C, n - first);
         const uint64_t in_bytes = round_up_u64(packed_payload_bytes(cnt, w), 16);
-        SSS_TRY(grow(&s.d_in, &s.in_cap, round_up_u64(packed_payload_bytes(C, w), 16) + 16));
-        SSS_TRY(grow(&s.d_out, &s.out_cap, C * 4));
+        SSS_TRY(grow(&s.d_in, &s.in_cap, in_cap));
+        SSS_TRY(grow(&s.d_out, &s.out_cap, Ca * 4));
         const uint8_t* src = static_cast<const uint8_t*>(h_packed) + first * (uint64_t)w / 8;
-        SSS_CK(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
+        SSS_TRY(pipe.copy_in(slot, src, in_bytes, in_cap));
         SSS_CK(launch_unpack(ctx->dev, s.d_in, cnt, w, static_cast<int32_t*>(s.d_out), s.stream));
-        SSS_CK(cudaMemcpyAsync(h_out + first, s.d_out, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+        if (pipe.out_staged())
+            SSS_TRY(pipe.copy_out_staged(slot, cnt * 4, Ca * 4, {{h_out + first, 0, cnt * 4}}));
+        else
+            SSS_CK(cudaMemcpyAsync(h_out + first, s.d_out, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
     }
-    for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
-    return SSS_OK;
+    return pipe.finish(slot);
 }
 
 int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, uint32_t lo, uint32_t hi,
@@ -516,24 +639,29 @@ int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, u
     const uint64_t n_eval = eval_codes_for(n, w, tail_granule);
     const uint64_t out_total = out_bytes_for(n, w, tail_granule);
     const uint64_t C = chunk_codes(w / 8.0, 1 / 8.0);
+    const uint64_t Ca = std::min<uint64_t>(C, round_up_u64(n_eval, 1024));
+    const size_t in_cap = round_up_u64(Ca / 32 * (uint64_t)w * 4, 16) + 16;
     SSS_CK(cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned long long), ctx->slots[0].stream));
     SSS_CK(cudaStreamSynchronize(ctx->slots[0].stream));
+    // (the bitvector is 1/8 byte per code: its pageable destination is served by the plain copy)
+    HostPipe pipe(ctx, is_pageable(h_packed), false);
     int slot = 0;
     for (uint64_t first = 0; first < n_eval; first += C, slot = (slot + 1) % kSlots) {
         Slot& s = ctx->slots[slot];
+        SSS_TRY(pipe.acquire(slot));
         const uint64_t cnt = std::min(C, n_eval - first);
         const uint64_t in_bytes = round_up_u64(((cnt + 31) / 32) * (uint64_t)w * 4, 16);
-        SSS_TRY(grow(&s.d_in, &s.in_cap, round_up_u64(C / 32 * (uint64_t)w * 4, 16) + 16));
-        SSS_TRY(grow(&s.d_out, &s.out_cap, C / 8));
+        SSS_TRY(grow(&s.d_in, &s.in_cap, in_cap));
+        SSS_TRY(grow(&s.d_out, &s.out_cap, Ca / 8 + 16));
         const uint8_t* src = static_cast<const uint8_t*>(h_packed) + first * (uint64_t)w / 8;
-        SSS_CK(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
+        SSS_TRY(pipe.copy_in(slot, src, in_bytes, in_cap));
         SSS_TRY(scan_range_impl(ctx, s.d_in, cnt, w, lo, hi, s.d_out, ctx->d_counts, true, s.stream));
         const uint64_t out_off = first / 8;
         const uint64_t out_bytes = std::min<uint64_t>(4 * ((cnt + 31) / 32), out_total - out_off);
         SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_bitvec) + out_off, s.d_out, out_bytes, cudaMemcpyDeviceToHost,
                                s.stream));
     }
-    for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
+    SSS_TRY(pipe.finish(slot));
     if (h_count) SSS_CK(cudaMemcpy(h_count, ctx->d_counts, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return SSS_OK;
 }
@@ -561,35 +689,26 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
     const bool single = K == 1;  // see single_predicate_body
     if (!single) SSS_CK(launch_build_pred_index(ctx->d_lo, ctx->d_hi, K, w, ctx->d_index, s0));
     SSS_CK(cudaStreamSynchronize(s0));
-    // Per-predicate destination vectors (h_out_ptrs): one device->host copy per chunk into the slot's
-    // pinned bounce buffer and a host-side scatter of the K pieces once the chunk has landed, instead
-    // of K small copies per chunk (1024 x 8 KB at K = 1024) into pageable memory.
-    struct Pending {
-        bool live = false;
-        uint64_t out_off = 0, piece = 0, stride = 0;
-    } pending[kSlots];
+    // Results go through the slot's pinned bounce buffer -- one device->host copy per chunk, then a
+    // host-side scatter once the chunk has landed -- when the destination is pageable, and always for
+    // per-predicate destination vectors (h_out_ptrs): K small copies per chunk (1024 x 8 KB at K = 1024)
+    // into pageable memory are what the reference's signature would otherwise cost.
+    const bool staged = h_out_ptrs != nullptr || is_pageable(h_out);
+    HostPipe pipe(ctx, is_pageable(h_packed), staged);
     const uint64_t chunk_stride = C / 8;  // device-side bitvector stride inside the slot (full chunks)
     const uint64_t Ca = std::min<uint64_t>(C, round_up_u64(n_eval, 1024));  // codes the staging buffers are sized for
-    auto drain = [&](int sl) -> int {
-        if (!pending[sl].live) return SSS_OK;
-        SSS_CK(cudaStreamSynchronize(ctx->slots[sl].stream));
-        const uint8_t* src = static_cast<const uint8_t*>(ctx->slots[sl].h_bounce);
-        for (int k = 0; k < K; k++)
-            std::memcpy(static_cast<uint8_t*>(h_out_ptrs[k]) + pending[sl].out_off, src + (uint64_t)k * pending[sl].stride,
-                        pending[sl].piece);
-        pending[sl].live = false;
-        return SSS_OK;
-    };
+    const size_t in_cap = round_up_u64(Ca / 32 * (uint64_t)w * 4, 16) + 16;
+    const size_t out_cap = (Ca / 8 + 128) * (uint64_t)K;
     int slot = 0;
     for (uint64_t first = 0; first < n_eval; first += C, slot = (slot + 1) % kSlots) {
         Slot& s = ctx->slots[slot];
-        if (h_out_ptrs != nullptr) SSS_TRY(drain(slot));  // the slot's previous chunk, before its buffers are reused
+        SSS_TRY(pipe.acquire(slot));  // the slot's previous chunk is delivered before its buffers are reused
         const uint64_t cnt = std::min(C, n_eval - first);
         const uint64_t in_bytes = round_up_u64(((cnt + 31) / 32) * (uint64_t)w * 4, 16);
-        SSS_TRY(grow(&s.d_in, &s.in_cap, round_up_u64(Ca / 32 * (uint64_t)w * 4, 16) + 16));
-        SSS_TRY(grow(&s.d_out, &s.out_cap, (Ca / 8 + 128) * (uint64_t)K));
+        SSS_TRY(grow(&s.d_in, &s.in_cap, in_cap));
+        SSS_TRY(grow(&s.d_out, &s.out_cap, out_cap));
         const uint8_t* src = static_cast<const uint8_t*>(h_packed) + first * (uint64_t)w / 8;
-        SSS_CK(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
+        SSS_TRY(pipe.copy_in(slot, src, in_bytes, in_cap));
         // a short (last) chunk packs its bitvectors tightly so that small columns do not move whole-chunk strides
         const uint64_t dev_stride = std::min(chunk_stride, round_up_u64(4 * ((cnt + 31) / 32), 128));
         if (single)
@@ -601,21 +720,25 @@ static int host_shared_impl(sss_ctx* ctx, bool linear, const void* h_packed, uin
         const uint64_t out_off = first / 8;  // bytes per predicate / rows already produced
         const uint64_t piece = std::min<uint64_t>(4 * ((cnt + 31) / 32), out_total - out_off);
         if (linear) {
-            SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_out) + out_off * (uint64_t)K, s.d_out, piece * (uint64_t)K,
-                                   cudaMemcpyDeviceToHost, s.stream));
-        } else if (h_out_ptrs != nullptr) {
-            SSS_TRY(grow_pinned(&s.h_bounce, &s.bounce_cap, (Ca / 8 + 128) * (uint64_t)K));
-            SSS_CK(cudaMemcpyAsync(s.h_bounce, s.d_out, (uint64_t)(K - 1) * dev_stride + piece, cudaMemcpyDeviceToHost,
-                                   s.stream));
-            pending[slot] = Pending{true, out_off, piece, dev_stride};
+            uint8_t* dst = static_cast<uint8_t*>(h_out) + out_off * (uint64_t)K;
+            if (staged)
+                SSS_TRY(pipe.copy_out_staged(slot, piece * (uint64_t)K, out_cap, {{dst, 0, piece * (uint64_t)K}}));
+            else
+                SSS_CK(cudaMemcpyAsync(dst, s.d_out, piece * (uint64_t)K, cudaMemcpyDeviceToHost, s.stream));
+        } else if (staged) {
+            std::vector<HostPipe::Piece> pieces((size_t)K);
+            for (int k = 0; k < K; k++) {
+                uint8_t* base = h_out_ptrs != nullptr ? static_cast<uint8_t*>(h_out_ptrs[k])
+                                                      : static_cast<uint8_t*>(h_out) + (uint64_t)k * stride_bytes;
+                pieces[k] = HostPipe::Piece{base + out_off, (size_t)((uint64_t)k * dev_stride), (size_t)piece};
+            }
+            SSS_TRY(pipe.copy_out_staged(slot, (uint64_t)(K - 1) * dev_stride + piece, out_cap, std::move(pieces)));
         } else {
             SSS_CK(cudaMemcpy2DAsync(static_cast<uint8_t*>(h_out) + out_off, stride_bytes, s.d_out, dev_stride, piece,
                                      (size_t)K, cudaMemcpyDeviceToHost, s.stream));
         }
     }
-    if (h_out_ptrs != nullptr)
-        for (int i = 0; i < kSlots; i++, slot = (slot + 1) % kSlots) SSS_TRY(drain(slot));  // oldest first
-    for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
+    SSS_TRY(pipe.finish(slot));
     if (h_counts) {
         if (!single && !counts_directly(linear, K))
             SSS_CK(launch_counts_from_histogram(ctx->d_index, K, ctx->d_counts, s0));
@@ -696,24 +819,31 @@ int sss_host_pack(sss_ctx* ctx, const uint32_t* h_codes, uint64_t n, int w, void
     SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     const size_t total = sss_packed_bytes(n, w);
-    std::memset(h_packed, 0, total);  // padding (and everything, for n == 0)
+    std::memset(static_cast<uint8_t*>(h_packed) + packed_payload_bytes(n, w), 0, total - packed_payload_bytes(n, w));
     const uint64_t C = chunk_codes(4.0, w / 8.0);
+    const uint64_t Ca = std::min<uint64_t>(C, round_up_u64(n, 1024));
+    const size_t out_cap = Ca / 32 * (uint64_t)w * 4 + 16;
+    HostPipe pipe(ctx, n != 0 && is_pageable(h_codes), is_pageable(h_packed));
     int slot = 0;
     for (uint64_t first = 0; first < n; first += C, slot = (slot + 1) % kSlots) {
         Slot& s = ctx->slots[slot];
+        SSS_TRY(pipe.acquire(slot));
         const uint64_t cnt = std::min(C, n - first);
         const uint64_t words = (cnt * (uint64_t)w + 31) / 32;
-        SSS_TRY(grow(&s.d_in, &s.in_cap, C * 4));
-        SSS_TRY(grow(&s.d_out, &s.out_cap, C / 32 * (uint64_t)w * 4 + 16));
-        SSS_CK(cudaMemcpyAsync(s.d_in, h_codes + first, cnt * 4, cudaMemcpyHostToDevice, s.stream));
+        SSS_TRY(grow(&s.d_in, &s.in_cap, Ca * 4));
+        SSS_TRY(grow(&s.d_out, &s.out_cap, out_cap));
+        SSS_TRY(pipe.copy_in(slot, h_codes + first, cnt * 4, Ca * 4));
         SSS_CK(launch_pack(ctx->dev, static_cast<const uint32_t*>(s.d_in), cnt, w, static_cast<uint32_t*>(s.d_out), words,
                            s.stream));
         const uint64_t off = first * (uint64_t)w / 8;
         const uint64_t bytes = std::min<uint64_t>(words * 4, total - off);
-        SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_packed) + off, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
+        uint8_t* dst = static_cast<uint8_t*>(h_packed) + off;
+        if (pipe.out_staged())
+            SSS_TRY(pipe.copy_out_staged(slot, bytes, out_cap, {{dst, 0, (size_t)bytes}}));
+        else
+            SSS_CK(cudaMemcpyAsync(dst, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
     }
-    for (auto& s : ctx->slots) SSS_CK(cudaStreamSynchronize(s.stream));
-    return SSS_OK;
+    return pipe.finish(slot);
 }
 
 void* sss_host_alloc(size_t bytes)

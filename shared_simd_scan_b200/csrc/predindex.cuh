@@ -384,6 +384,28 @@ __device__ __forceinline__ uint32_t locator_entry(const PredIndexView& ix, uint3
     return v;
 }
 
+// Left-aligned code with the shift of a non-straddling code issued as a MULTIPLY by a power of two that
+// ptxas cannot see (constant bank): written as `x << a`, ptxas merges it with the `>> 19` of the bucket
+// index into `(x >> b) & 0x1fff` -- two ALU-pipe instructions (SHF + LOP3) where IMAD (FMA pipe) + SHF do,
+// and the ALU pipe is the one these kernels are short of (ncu: ALU 67 %, FMA 16 % at K = 64).
+#ifndef SSS_LOCATE_FMA
+#define SSS_LOCATE_FMA 1
+#endif
+static __constant__ uint32_t c_pow2[32] = {
+    1u << 0,  1u << 1,  1u << 2,  1u << 3,  1u << 4,  1u << 5,  1u << 6,  1u << 7,  1u << 8,  1u << 9,  1u << 10,
+    1u << 11, 1u << 12, 1u << 13, 1u << 14, 1u << 15, 1u << 16, 1u << 17, 1u << 18, 1u << 19, 1u << 20, 1u << 21,
+    1u << 22, 1u << 23, 1u << 24, 1u << 25, 1u << 26, 1u << 27, 1u << 28, 1u << 29, 1u << 30, 1u << 31};
+
+template <int W, int J>
+__device__ __forceinline__ uint32_t located_code(const uint32_t (&x)[W])
+{
+#if SSS_LOCATE_FMA
+    constexpr CodeSlot s = code_slot(W, J);
+    if constexpr (s.end_shift != 32 && !s.straddles) return x[s.last_word] * c_pow2[32 - s.end_shift];
+#endif
+    return left_aligned_code<W, J>(x);
+}
+
 template <int W, int J>
 struct BlockIds {
     static __device__ __forceinline__ void fast(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&id)[32],
@@ -437,7 +459,7 @@ struct BlockRows {
     static __device__ __forceinline__ void fast(const uint32_t (&x)[W], const PredIndexView& ix, uint32_t (&row)[32],
                                                 uint32_t& flags)
     {
-        const uint32_t t = left_aligned_code<W, J>(x);
+        const uint32_t t = located_code<W, J>(x);
         if constexpr (W <= kDirectMaxW) {
             row[J] = locator_entry(ix, t >> (32 - W)) * ix.row_bytes + ix.rows_saddr;
         } else {
@@ -542,6 +564,18 @@ __device__ __forceinline__ T* ptr_add_fma(T* base, uint32_t off_bytes)
 {
     uint64_t a;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(off_bytes), "r"(c_one), "l"(base));
+    return reinterpret_cast<T*>(a);
+}
+
+// base + k * stride as ONE IMAD.WIDE (FMA pipe), k = 0..31 read from the constant bank so that ptxas
+// can neither fold it nor strength-reduce the 32 addresses of a column into a 64-bit add chain
+static __constant__ uint32_t c_iota[32] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15,
+                                           16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31};
+template <class T>
+__device__ __forceinline__ T* ptr_mad_fma(T* base, uint32_t stride_bytes, int k)
+{
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(stride_bytes), "r"(c_iota[k]), "l"(base));
     return reinterpret_cast<T*>(a);
 }
 

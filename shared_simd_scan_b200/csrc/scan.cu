@@ -31,6 +31,16 @@
 
 namespace sss {
 
+// developer switch: plain instead of streaming (evict-first) stores of the result words
+#ifndef SSS_SCAN_PLAINST
+#define SSS_SCAN_PLAINST 0
+#endif
+#if SSS_SCAN_PLAINST
+#define SSS_SCAN_ST(p, v) (*(p) = (v))
+#else
+#define SSS_SCAN_ST(p, v) __stcs((p), (v))
+#endif
+
 enum ScanMode : int { kScalar = 0, kSwarLoTop0 = 1, kSwarLoTop1 = 2, kOneBit = 3 };
 
 template <int W>
@@ -170,13 +180,13 @@ __device__ __forceinline__ uint32_t scan_tile(const uint32_t* buf, const ScanArg
         }
         uint32_t* dst = tile_out + b0;
         if (P::kG == 4 && (!kChecked || b0 + 4 <= blocks_left)) {
-            __stcs(reinterpret_cast<uint4*>(dst), make_uint4(res[0], res[1 % P::kG], res[2 % P::kG], res[3 % P::kG]));
+            SSS_SCAN_ST(reinterpret_cast<uint4*>(dst), make_uint4(res[0], res[1 % P::kG], res[2 % P::kG], res[3 % P::kG]));
         } else if (P::kG == 2 && (!kChecked || b0 + 2 <= blocks_left)) {
-            __stcs(reinterpret_cast<uint2*>(dst), make_uint2(res[0], res[1 % P::kG]));
+            SSS_SCAN_ST(reinterpret_cast<uint2*>(dst), make_uint2(res[0], res[1 % P::kG]));
         } else {
 #pragma unroll
             for (int b = 0; b < P::kG; b++)
-                if (!kChecked || b0 + b < blocks_left) st_stream_u32(dst + b, res[b]);
+                if (!kChecked || b0 + b < blocks_left) SSS_SCAN_ST(dst + b, res[b]);
         }
     }
     return hits;

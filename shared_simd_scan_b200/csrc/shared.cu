@@ -29,6 +29,29 @@ namespace sss {
 #define SSS_SHARED_THREADS 512
 #endif
 constexpr int kSThreads = SSS_SHARED_THREADS;
+#ifndef SSS_STORE_FMA
+#define SSS_STORE_FMA 0
+#endif
+// knock-out switches for bottleneck hunting (results are WRONG with any of them set; never shipped):
+// SSS_KO_STORES: only predicate 0 of a column is stored; SSS_KO_ATOMS: no interval counting;
+// SSS_KO_TRANSPOSE: mask words stored untransposed; SSS_KO_PLAINST: plain instead of streaming stores
+#ifndef SSS_KO_STORES
+#define SSS_KO_STORES 0
+#endif
+#ifndef SSS_KO_ATOMS
+#define SSS_KO_ATOMS 0
+#endif
+#ifndef SSS_KO_TRANSPOSE
+#define SSS_KO_TRANSPOSE 0
+#endif
+#ifndef SSS_KO_PLAINST
+#define SSS_KO_PLAINST 0
+#endif
+#if SSS_KO_PLAINST
+#define SSS_ST(p, v) (*(p) = (v))
+#else
+#define SSS_ST(p, v) st_stream_u32((p), (v))
+#endif
 
 template <int W>
 struct SharedCfg {
@@ -123,7 +146,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
             }
         }
         if constexpr (!kSmem) rows_of_ids<kSmem>(ix, id);
-        if (kSmem && count_matches) {  // the rows carry their interval's counter
+        if (kSmem && count_matches && !SSS_KO_ATOMS) {  // the rows carry their interval's counter
             if (!last) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) row_count(id[j]);
@@ -139,15 +162,32 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
             const uint32_t col_bytes = kSmem ? (((uint32_t)c + plan.has_counter) << (plan.rep_log2 + 2)) : (uint32_t)c * 4u;
 #pragma unroll
             for (int j = 0; j < 32; j++) m[j] = row_mask_word<kSmem>(ix, id[j], col_bytes);
+#if !SSS_KO_TRANSPOSE
             transpose32(m);  // m[k'] bit j = predicate 32c+k' on code j
+#endif
             const int kk = K - 32 * c;  // predicates in this column
+#if SSS_KO_STORES
+            {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int k = 0; k < 32; k++) acc ^= m[k];
+                SSS_ST(p, acc);
+                p += 32 * stride_words;
+                continue;
+            }
+#endif
             if (kk >= 32 && !last && !Rot::kRot && narrow) {
                 // address of predicate k's word = p + k * stride: one IMAD.WIDE each (FMA pipe) instead of
                 // a 64-bit add chain (two ALU instructions per store)
+#if SSS_STORE_FMA
+#pragma unroll
+                for (int k = 0; k < 32; k++) st_stream_u32(ptr_mad_fma(p, stride_bytes32, k), m[k]);
+#else
 #pragma unroll
                 for (int k = 0; k < 32; k++)
-                    st_stream_u32(reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p) +
-                                                              (uint64_t)stride_bytes32 * (uint32_t)k), m[k]);
+                    SSS_ST(reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p) + (uint64_t)stride_bytes32 * (uint32_t)k),
+                           m[k]);
+#endif
                 p += 32 * stride_words;
             } else if (kk >= 32 && !last && !Rot::kRot) {
 #pragma unroll
