@@ -139,6 +139,8 @@ int sss_unpack_at(sss_ctx* ctx, const void* d_packed, int w, const uint64_t* d_p
 #define SSS_CALIB_WRITE 1
 #define SSS_CALIB_COPY 2
 #define SSS_CALIB_MIX 3
+#define SSS_CALIB_STREAMS32 4   /* writes `bytes` to d_b as `ratio` = K interleaved output streams, 32-bit stores: */
+#define SSS_CALIB_STREAMS128 5  /* the shared scan's bitvector write pattern without its computation (128-bit stores) */
 int sss_calibrate(sss_ctx* ctx, int mode, const void* d_a, void* d_b, uint64_t bytes, uint32_t ratio, void* stream);
 
 /* shared_scan_* (src/simd_scan_shared.cpp:9-466): K bitvectors, predicate k's at

@@ -250,7 +250,7 @@ def decompress_at(packed: torch.Tensor, w: int, positions: torch.Tensor, num: Op
     return out[:num]
 
 
-_CALIB = {"read": 0, "write": 1, "copy": 2, "mix": 3}
+_CALIB = {"read": 0, "write": 1, "copy": 2, "mix": 3, "streams32": 4, "streams128": 5}
 
 
 def calibrate(mode: str, a: Optional[torch.Tensor], b: Optional[torch.Tensor], nbytes: int, ratio: int = 1) -> None:

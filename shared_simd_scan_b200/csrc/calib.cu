@@ -61,11 +61,56 @@ calib_kernel(int mode, const uint4* __restrict__ a, uint4* __restrict__ b, uint6
     }
 }
 
+// mode STREAMS32 / STREAMS128: the WRITE pattern of the shared scan's bitvector layout without any of
+// its computation -- `ratio` = K independent output streams of bytes/K each; a 512-thread CTA owns tiles
+// of 512 (x4) consecutive words and writes its piece of EVERY stream, one 32-bit (128-bit) store per
+// thread and stream, streams innermost (exactly the order shared_scan_kernel stores in).  Tells apart
+// "the memory system dislikes K x 148 interleaved 2 KB runs" from "the kernel does not overlap".
+template <int kVec>
+__global__ void __launch_bounds__(512)
+calib_streams_kernel(const uint4* __restrict__ a, uint32_t read_vec_per_thread, uint32_t* __restrict__ b,
+                     uint64_t stream_words, uint32_t K)
+{
+    const uint64_t tile_words = 512ull * kVec;
+    const uint64_t tiles = stream_words / tile_words;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        uint32_t* p = b + tile * tile_words + (uint64_t)threadIdx.x * kVec;
+        uint32_t v = (uint32_t)tile ^ threadIdx.x;
+        if (a != nullptr) {  // the scan's input side: read_vec_per_thread x 16 bytes per thread and tile, contiguous per tile
+            const uint4* src = a + tile * 512ull * read_vec_per_thread + threadIdx.x;
+            for (uint32_t r = 0; r < read_vec_per_thread; r++) {
+                const uint4 q = __ldcs(src + r * 512u);
+                v ^= q.x ^ q.y ^ q.z ^ q.w;
+            }
+        }
+#pragma unroll 8
+        for (uint32_t k = 0; k < K; k++) {
+            if constexpr (kVec == 4) __stcs(reinterpret_cast<uint4*>(p), make_uint4(v, k, v, k));
+            else __stcs(p, v + k);
+            p += stream_words;
+        }
+    }
+}
+
 cudaError_t launch_calibrate(const Device& dev, int mode, const void* a, void* b, uint64_t bytes, uint32_t ratio,
                              unsigned long long* sink, cudaStream_t stream)
 {
     const uint64_t n_vec = bytes / 16;
     if (n_vec == 0) return cudaSuccess;
+    if (mode == 4 || mode == 5) {
+        const uint32_t K = ratio == 0 ? 1 : ratio;
+        const uint64_t stream_words = bytes / 4 / K / 2048 * 2048;
+        if (stream_words == 0) return cudaSuccess;
+        // with d_a given, every thread also reads 4 x 16 bytes per tile (the packed input of ~16-bit codes)
+        const uint32_t rv = a != nullptr ? (mode == 4 ? 4u : 16u) : 0u;
+        if (mode == 4)
+            calib_streams_kernel<1><<<dev.sm_count, 512, 0, stream>>>(static_cast<const uint4*>(a), rv, static_cast<uint32_t*>(b),
+                                                                      stream_words, K);
+        else
+            calib_streams_kernel<4><<<dev.sm_count, 512, 0, stream>>>(static_cast<const uint4*>(a), rv, static_cast<uint32_t*>(b),
+                                                                      stream_words, K);
+        return cudaGetLastError();
+    }
     // grid: 8 CTAs per SM; for MIX the vectors a round covers must divide by the ratio -> round the grid
     unsigned grid = (unsigned)dev.sm_count * 8;
     if (mode == 3 && ratio > 1) grid = grid / ratio * ratio;

@@ -505,10 +505,11 @@ int sss_unpack_at(sss_ctx* ctx, const void* d_packed, int w, const uint64_t* d_p
 
 int sss_calibrate(sss_ctx* ctx, int mode, const void* d_a, void* d_b, uint64_t bytes, uint32_t ratio, void* stream)
 {
-    if (ctx == nullptr || mode < SSS_CALIB_READ || mode > SSS_CALIB_MIX) return SSS_ERR_INVALID_ARG;
-    if (mode != SSS_CALIB_WRITE && (d_a == nullptr || (reinterpret_cast<uintptr_t>(d_a) & 15))) return SSS_ERR_INVALID_ARG;
+    if (ctx == nullptr || mode < SSS_CALIB_READ || mode > SSS_CALIB_STREAMS128) return SSS_ERR_INVALID_ARG;
+    if (mode != SSS_CALIB_WRITE && mode < SSS_CALIB_STREAMS32 && (d_a == nullptr || (reinterpret_cast<uintptr_t>(d_a) & 15))) return SSS_ERR_INVALID_ARG;
     if (mode != SSS_CALIB_READ && (d_b == nullptr || (reinterpret_cast<uintptr_t>(d_b) & 15))) return SSS_ERR_INVALID_ARG;
     if (mode == SSS_CALIB_MIX && (ratio == 0 || ratio > 64)) return SSS_ERR_INVALID_ARG;
+    if (mode >= SSS_CALIB_STREAMS32 && (ratio == 0 || ratio > SSS_MAX_PREDICATES)) return SSS_ERR_INVALID_ARG;
     SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     return cuda_status(launch_calibrate(ctx->dev, mode, d_a, d_b, bytes, ratio, ctx->d_counts + SSS_MAX_PREDICATES,

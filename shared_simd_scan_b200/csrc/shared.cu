@@ -47,6 +47,13 @@ constexpr int kSThreads = SSS_SHARED_THREADS;
 #ifndef SSS_KO_PLAINST
 #define SSS_KO_PLAINST 0
 #endif
+// SSS_KO_LOCATE: row handles from the code's low bits, no locator lookup; SSS_KO_MASKLD: no mask loads
+#ifndef SSS_KO_LOCATE
+#define SSS_KO_LOCATE 0
+#endif
+#ifndef SSS_KO_MASKLD
+#define SSS_KO_MASKLD 0
+#endif
 #if SSS_KO_PLAINST
 #define SSS_ST(p, v) (*(p) = (v))
 #else
@@ -68,9 +75,26 @@ struct SharedCfg {
 // through the interval histogram (one shared-memory atomic per code, independent of K).
 static_assert(kDirectCountMaxK == 8, "the K <= 8 path of shared_scan_kernel is the direct-count path");
 
+// Wide stores (kWide).  A thread's 32 result words of a column belong to 32 different bitvectors, so
+// the natural store is one 32-bit word per thread and predicate: 128 bytes per warp instruction.  The
+// SM sustains far fewer bytes of such narrow stores next to other traffic than of 128-bit stores
+// (tools/probes/stream_pattern.py: 64 output streams + the column's reads: 4.3 TB/s with 32-bit stores,
+// 5.5 TB/s with 128-bit stores; knocking the stores out of this kernel made it 1.65x faster while
+// knocking out the transposes, the lookups or the counting changed nothing, profiles/r02_knockouts.txt).
+// So a warp parks the 32 x 32 words of a column in a warp-private shared-memory stage [predicate][block]
+// (conflict-free 32-bit stores), and reads them back as 128-bit pieces along the BLOCK axis: lane
+// (k mod 4, q) gets words 4q..4q+3 of predicate k and writes them with ONE 128-bit store -- 8 store
+// instructions per column and thread instead of 32, four full 128-byte lines each.
+// kStage = predicates a warp parks per round (32 / kStage rounds per column): 32 -> 4 KB per warp (64 KB per
+// CTA), 16 -> 2 KB (32 KB); 0 = narrow stores.  The stage competes with the lane-private table replicas for
+// shared memory, so the launcher picks the largest stage that costs no (32) or at most one (16) halving
+// of the row-table replicas (profiles/r02_ab_wide_v2.txt, K = 64: 17-19 bit 0.73 -> 0.80, 20-31 bit 0.75 ->
+// 0.78-0.82, 10-13 bit 0.71 -> 0.79; K = 256 / 512: 0.61 -> 0.70).
+SSS_HD constexpr int stage_bytes(int k_stage) { return (kSThreads / 32) * k_stage * 32 * 4; }
+
 // kSmem: merged row table in shared memory (otherwise the masks are read through L1 from global
 // memory and the interval histogram is a separate shared-memory array)
-template <int W, bool kSmem>
+template <int W, bool kSmem, int kStage>
 __global__ void __launch_bounds__(kSThreads, 1)
 shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                    const uint8_t* __restrict__ g_index, int K, uint32_t* __restrict__ bitvecs, uint64_t stride_words,
@@ -79,8 +103,12 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
     using Cfg = SharedCfg<W>;
     using Rot = BlockRot<W, 1>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* s_index = smem + Cfg::kRingBytes + plan.hist_bytes;
-    const IntervalHist hist = hist_init(smem + Cfg::kRingBytes, plan);  // kSmem: empty, the rows carry the counters
+    constexpr bool kWide = kStage > 0;
+    constexpr int kStagePreds = kStage;
+    constexpr int kFront = Cfg::kRingBytes + stage_bytes(kStage);  // ring, then the wide-store stage
+    uint32_t* const stage = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes) + (threadIdx.x >> 5) * (kStage * 32);
+    uint8_t* s_index = smem + kFront + plan.hist_bytes;
+    const IntervalHist hist = hist_init(smem + kFront, plan);  // kSmem: empty, the rows carry the counters
     const PredIndexView ix = load_pred_index(g_index, s_index, plan);
     typename Cfg::Ring ring(smem, packed, readable_bytes16);
     ring.start();  // contains the __syncthreads that publishes the index and the zeroed counters
@@ -108,13 +136,22 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
 #pragma unroll
         for (int k = 0; k < W; k++) loaded |= x[k];
         ring.release_warp(iter, tile, loaded);  // the stage is free once every warp has copied its words
-        if (!active) continue;
+        // kWide: the warp exchanges its result words through shared memory, so lanes past the column's end
+        // stay with their warp (their lookups run on whatever the tile holds -- every index stays inside the
+        // tables --, they count nothing and store nothing)
+        const uint64_t gb_warp0 = gb - (threadIdx.x & 31);
+        if (kWide ? gb_warp0 >= n_blocks : !active) continue;
 
         const uint32_t unrot = rot * Rot::kPieceCodes;
         const uint32_t keep = last ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
         uint32_t id[32];
+#if SSS_KO_LOCATE
+#pragma unroll
+        for (int j = 0; j < 32; j++) id[j] = ((x[j % W] >> (j & 15)) & 63u) * ix.row_bytes + ix.rows_saddr;
+#else
         if constexpr (kSmem) block_rows<W>(x, ix, id);  // row handles directly
         else block_ids<W>(x, ix, id);
+#endif
         uint32_t* p = bitvecs + gb;  // this block's word of predicate 0; += stride_words per predicate
         if (K <= kDirectCountMaxK) {  // one byte of predicates per code: the cheap 32 x 8 transpose
             if constexpr (!kSmem) rows_of_ids<kSmem>(ix, id);
@@ -122,6 +159,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
 #pragma unroll
             for (int j = 0; j < 32; j++) m[j] = row_mask_word<kSmem>(ix, id[j], 0);  // (no counter column: K <= 8)
             transpose32x8(m, r);
+            if (kWide && !active) continue;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 if (k < K) {
@@ -135,7 +173,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
             }
             continue;
         }
-        if (!kSmem && count_matches) {  // separate histogram, indexed by the interval id
+        if (!kSmem && count_matches && active) {  // separate histogram, indexed by the interval id
             if (!last) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) hist.add(id[j]);
@@ -146,7 +184,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
             }
         }
         if constexpr (!kSmem) rows_of_ids<kSmem>(ix, id);
-        if (kSmem && count_matches && !SSS_KO_ATOMS) {  // the rows carry their interval's counter
+        if (kSmem && count_matches && active && !SSS_KO_ATOMS) {  // the rows carry their interval's counter
             if (!last) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) row_count(id[j]);
@@ -160,8 +198,13 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
             uint32_t m[32];
             // derived from the kernel parameter so that it stays in a uniform register: LDS [R + UR]
             const uint32_t col_bytes = kSmem ? (((uint32_t)c + plan.has_counter) << (plan.rep_log2 + 2)) : (uint32_t)c * 4u;
+#if SSS_KO_MASKLD
+#pragma unroll
+            for (int j = 0; j < 32; j++) m[j] = id[j] * 2654435761u + col_bytes;
+#else
 #pragma unroll
             for (int j = 0; j < 32; j++) m[j] = row_mask_word<kSmem>(ix, id[j], col_bytes);
+#endif
 #if !SSS_KO_TRANSPOSE
             transpose32(m);  // m[k'] bit j = predicate 32c+k' on code j
 #endif
@@ -176,6 +219,49 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
                 continue;
             }
 #endif
+            if constexpr (kWide) {
+                const uint32_t lane = threadIdx.x & 31;
+                const uint32_t live = active ? keep : 0u;
+                const uint32_t kq = lane >> 3, q4 = (lane & 7) * 4;
+                const uint64_t gbq = gb_warp0 + q4;  // first of the 4 consecutive blocks this lane stores
+                uint32_t* pw = bitvecs + (uint64_t)(32 * c + (int)kq) * stride_words + gbq;
+                const uint32_t* src = stage + kq * 32 + q4;
+                const bool whole = kk >= 32 && gb_warp0 + 32 <= n_blocks;  // warp-uniform
+#pragma unroll
+                for (int r0 = 0; r0 < 32; r0 += (kWide ? kStagePreds : 32)) {  // rounds of kStagePreds predicates
+                    __syncwarp();  // the previous round's wide reads of the stage are done
+#pragma unroll
+                    for (int k = 0; k < kStagePreds; k++) {
+                        uint32_t v = m[r0 + k];
+                        if constexpr (Rot::kRot) v = __funnelshift_l(v, v, unrot);
+                        stage[k * 32 + lane] = v & live;
+                    }
+                    __syncwarp();
+                    if (whole) {
+#pragma unroll
+                        for (int i = 0; i < kStagePreds / 4; i++) {
+                            __stcs(reinterpret_cast<uint4*>(pw), *reinterpret_cast<const uint4*>(src + i * 128));
+                            pw += 4 * stride_words;
+                        }
+                    } else {  // the last predicates of a ragged K, or the last warp of the column
+#pragma unroll
+                        for (int i = 0; i < kStagePreds / 4; i++) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(src + i * 128);
+                            if (r0 + (int)kq + 4 * i < kk) {
+                                if (gbq + 4 <= n_blocks) {
+                                    __stcs(reinterpret_cast<uint4*>(pw), v);
+                                } else {
+                                    if (gbq + 0 < n_blocks) st_stream_u32(pw + 0, v.x);
+                                    if (gbq + 1 < n_blocks) st_stream_u32(pw + 1, v.y);
+                                    if (gbq + 2 < n_blocks) st_stream_u32(pw + 2, v.z);
+                                }
+                            }
+                            pw += 4 * stride_words;
+                        }
+                    }
+                }
+                continue;
+            }
             if (kk >= 32 && !last && !Rot::kRot && narrow) {
                 // address of predicate k's word = p + k * stride: one IMAD.WIDE each (FMA pipe) instead of
                 // a 64-bit add chain (two ALU instructions per store)
@@ -217,7 +303,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
         } else if (kSmem) {
             merged_hist_flush(ix, plan, s_index, g_index);
         } else {
-            hist_flush(smem + Cfg::kRingBytes, plan, ix.num_bp, g_index);
+            hist_flush(smem + kFront, plan, ix.num_bp, g_index);
         }
     }
 }
@@ -377,17 +463,17 @@ static cudaError_t launch_wide(const Device& dev, const void* packed, uint64_t n
     return cudaGetLastError();
 }
 
-template <int W, bool kSmem>
+template <int W, bool kSmem, int kStage>
 static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, const void* index, int K,
                              uint32_t* bitvecs, uint64_t stride_words, unsigned long long* counts, bool count_matches,
                              const IndexSmemPlan& plan, cudaStream_t stream)
 {
     using Cfg = SharedCfg<W>;
-    const size_t smem = Cfg::kRingBytes + plan.total_bytes;
+    const size_t smem = Cfg::kRingBytes + stage_bytes(kStage) + plan.total_bytes;
     static size_t configured[64] = {};
     if (configured[dev.ordinal & 63] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(shared_scan_kernel<W, kSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(shared_scan_kernel<W, kSmem, kStage>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev.ordinal & 63] = smem;
     }
@@ -396,10 +482,53 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    shared_scan_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(packed, readable, n,
-                                                                   static_cast<const uint8_t*>(index), K, bitvecs,
-                                                                   stride_words, counts, count_matches, plan);
+    shared_scan_kernel<W, kSmem, kStage><<<grid, kSThreads, smem, stream>>>(
+        packed, readable, n, static_cast<const uint8_t*>(index), K, bitvecs, stride_words, counts, count_matches, plan);
     return cudaGetLastError();
+}
+
+// Wide stores need every bitvector 16-byte aligned (base and stride) and at least one full column of
+// predicates; below 10 bits the kernel is closer to its instruction budget than to its store budget and
+// the narrow stores measured 1-2 % faster.
+#ifndef SSS_SHARED_WIDE
+#define SSS_SHARED_WIDE 1
+#endif
+#ifndef SSS_WIDE_MIN_K
+#define SSS_WIDE_MIN_K 32
+#endif
+#ifndef SSS_WIDE_MIN_W
+#define SSS_WIDE_MIN_W 10
+#endif
+static bool wide_ok(int W, int K, const uint32_t* bitvecs, uint64_t stride_words)
+{
+    return SSS_SHARED_WIDE && W >= SSS_WIDE_MIN_W && K >= SSS_WIDE_MIN_K && (reinterpret_cast<uintptr_t>(bitvecs) & 15) == 0 &&
+           (stride_words & 3) == 0;
+}
+
+template <int W>
+static IndexSmemPlan thread_plan(int K, int k_stage)
+{
+    return plan_index_smem(K, W, SharedCfg<W>::kRingBytes + stage_bytes(k_stage), /*use_hist=*/K > kDirectCountMaxK,
+                           /*merged_ok=*/true);
+}
+
+// the stage to use for K predicates at W bits (0: narrow stores) and the plan that goes with it
+template <int W>
+static int pick_stage(int K, bool wide_possible, IndexSmemPlan& plan)
+{
+    plan = thread_plan<W>(K, 0);
+    if (!wide_possible || !plan.merged) return 0;
+    const IndexSmemPlan p32 = thread_plan<W>(K, 32);
+    if (p32.merged && p32.rep_log2 == plan.rep_log2) {
+        plan = p32;
+        return 32;
+    }
+    const IndexSmemPlan p16 = thread_plan<W>(K, 16);
+    if (p16.merged && p16.rep_log2 + 1 >= plan.rep_log2) {
+        plan = p16;
+        return 16;
+    }
+    return 0;
 }
 
 template <int W>
@@ -407,8 +536,8 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, c
                             uint32_t* bitvecs, uint64_t stride_words, unsigned long long* counts, bool count_matches,
                             cudaStream_t stream)
 {
-    const IndexSmemPlan plan =
-        plan_index_smem(K, W, SharedCfg<W>::kRingBytes, /*use_hist=*/K > kDirectCountMaxK, /*merged_ok=*/true);
+    IndexSmemPlan plan;
+    const int k_stage = pick_stage<W>(K, wide_ok(W, K, bitvecs, stride_words), plan);
     // many predicates whose row table does not fit in shared memory: the warp-per-block kernel
     // (measured at K = 1024: 18 G codes/s at every width, against 26 G for the thread-per-block kernel
     // while the table fits -- W <= 9 -- and 5-12 G once it reads its rows from global memory)
@@ -419,9 +548,14 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, c
             return launch_wide<W, true>(dev, packed, n, index, K, bitvecs, stride_words, count_matches, wp, stream);
         return launch_wide<W, false>(dev, packed, n, index, K, bitvecs, stride_words, count_matches, wp, stream);
     }
-    if (plan.masks_in_smem)
-        return launch_ws<W, true>(dev, packed, n, index, K, bitvecs, stride_words, counts, count_matches, plan, stream);
-    return launch_ws<W, false>(dev, packed, n, index, K, bitvecs, stride_words, counts, count_matches, plan, stream);
+    if (plan.masks_in_smem) {
+        if (k_stage == 32)
+            return launch_ws<W, true, 32>(dev, packed, n, index, K, bitvecs, stride_words, counts, count_matches, plan, stream);
+        if (k_stage == 16)
+            return launch_ws<W, true, 16>(dev, packed, n, index, K, bitvecs, stride_words, counts, count_matches, plan, stream);
+        return launch_ws<W, true, 0>(dev, packed, n, index, K, bitvecs, stride_words, counts, count_matches, plan, stream);
+    }
+    return launch_ws<W, false, 0>(dev, packed, n, index, K, bitvecs, stride_words, counts, count_matches, plan, stream);
 }
 
 using Launcher = cudaError_t (*)(const Device&, const void*, uint64_t, const void*, int, uint32_t*, uint64_t,
@@ -444,10 +578,7 @@ static constexpr auto make_table(std::integer_sequence<int, Ws...>)
 template <int W>
 static int group_w(int K)
 {
-    auto merged = [](int k) {
-        return plan_index_smem(k, W, SharedCfg<W>::kRingBytes, /*use_hist=*/k > kDirectCountMaxK, /*merged_ok=*/true)
-                   .merged != 0;
-    };
+    auto merged = [](int k) { return thread_plan<W>(k, 0).merged != 0; };
     if (K <= 128 || merged(K)) return K;
     for (int g = 512; g >= 128; g >>= 1)
         if (g < K && merged(g)) return g;

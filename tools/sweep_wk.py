@@ -69,7 +69,7 @@ def main():
         packed = api.generate_packed(n, w, seed=42 + w)
         for K in ks:
             n2 = n
-            while K * (n2 // 8) > max_out:
+            while K * (n2 // 8 + int(os.environ.get("SSS_STRIDE_PAD", "0")) + 160) > max_out:
                 n2 //= 2
             g = torch.Generator().manual_seed(42 + K)
             lo = torch.randint(0, m + 1, (K,), generator=g)
@@ -78,7 +78,7 @@ def main():
             cnt = torch.empty(K, dtype=torch.int64, device="cuda")
             for op in ops:
                 if op == "shared":
-                    stride = (api.bitvec_bytes(n2) + 127) // 128 * 128
+                    stride = (api.bitvec_bytes(n2) + 127) // 128 * 128 + int(os.environ.get("SSS_STRIDE_PAD", "0"))
                     out = arena[: K * stride].view(K, stride)
                     f = lambda: api.shared_scan(packed, n2, w, lo_d, hi_d, out=out, counts=cnt)  # noqa: E731
                 else:
