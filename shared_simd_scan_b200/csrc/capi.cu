@@ -304,7 +304,9 @@ int sss_ctx_create(int device, sss_ctx** out)
     if (prop.major < 10) return SSS_ERR_UNSUPPORTED;  // kernels are sm_100a only
     sss_ctx* ctx = new (std::nothrow) sss_ctx();
     if (ctx == nullptr) return SSS_ERR_CUDA_BASE + (int)cudaErrorMemoryAllocation;
-    ctx->dev = Device{device, prop.multiProcessorCount, (int)prop.sharedMemPerBlockOptin};
+    ctx->dev.ordinal = device;
+    ctx->dev.sm_count = prop.multiProcessorCount;
+    ctx->dev.smem_optin = (int)prop.sharedMemPerBlockOptin;
     for (auto& s : ctx->slots) {
         cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
@@ -316,6 +318,8 @@ int sss_ctx_create(int device, sss_ctx** out)
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_hi, SSS_MAX_PREDICATES * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counts, (SSS_MAX_PREDICATES + 1) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_index, pred_index_bytes());
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dev.ticket_pool, kTicketSlots * 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->dev.ticket_pool, 0, kTicketSlots * 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_count_slots, kCountSlots * 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_count_slots, 0, kCountSlots * 2 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
@@ -343,6 +347,7 @@ int sss_ctx_destroy(sss_ctx* ctx)
     if (ctx->d_ws) cudaFree(ctx->d_ws);
     if (ctx->d_index) cudaFree(ctx->d_index);
     if (ctx->d_count_slots) cudaFree(ctx->d_count_slots);
+    if (ctx->dev.ticket_pool) cudaFree(ctx->dev.ticket_pool);
     delete ctx;
     return SSS_OK;
 }

@@ -98,17 +98,26 @@ __device__ __forceinline__ void st_v8_u32(void* p, const uint32_t (&w)[8])
 }
 
 // streaming stores: results are written once and never re-read by these kernels
+// (-DSSS_PLAIN_STORES=1: developer switch, plain stores everywhere these helpers are used)
+#ifndef SSS_PLAIN_STORES
+#define SSS_PLAIN_STORES 0
+#endif
+#if SSS_PLAIN_STORES
+__device__ __forceinline__ void st_stream_u32(uint32_t* p, uint32_t v) { *p = v; }
+__device__ __forceinline__ void st_stream_v4(int4* p, int4 v) { *p = v; }
+#else
 __device__ __forceinline__ void st_stream_u32(uint32_t* p, uint32_t v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream_v4(int4* p, int4 v) { __stcs(p, v); }
+#endif
 
 // ---- tile ring --------------------------------------------------------------------------------
 //
 // The packed column is cut into tiles of kTileBytes contiguous bytes (a whole number of 32-code
-// blocks, so every tile starts 16-byte aligned for any w).  CTA b owns tiles b, b+grid, b+2*grid...
-// Thread 0 keeps kStages bulk copies in flight; all threads wait on the stage's "full" mbarrier,
-// consume the tile from shared memory, meet at __syncthreads, and thread 0 refills the stage.
+// blocks, so every tile starts 16-byte aligned for any w).  Persistent CTAs draw tiles from a ticket
+// counter (below); kStages bulk copies are kept in flight; all threads wait on the stage's "full"
+// mbarrier, consume the tile from shared memory, and whoever releases the stage last refills it.
 //
-// Shared memory layout: [kStages][kTileBytes + kPadBytes] then kStages mbarriers.
+// Shared memory layout: [kStages][kTileBytes + kPadBytes], kStages mbarriers, kStages tile numbers.
 // Ring depth.  Measured on B200 (profiles/r01_ring_depth_ab.txt): with two CTAs per SM the scan
 // peaks with about 64 KB of ring per CTA (~100 KB of loads in flight per SM); deeper rings are
 // SLOWER (104 KB per CTA costs 5-10 % at W = 8..17), shallower ones starve.  2..8 stages.
@@ -121,25 +130,50 @@ constexpr int ring_stages(int tile_bytes)
     return fit < 2 ? 2 : (fit > 8 ? 8 : fit);
 }
 
-template <int kTileBytes, int kStages, int kPadBytes = 16>
+// Tile order.  Round 1 gave CTA b the tiles b, b + grid, b + 2 grid, ... (static round-robin).  A
+// persistent copy kernel written that way reaches 5.9-6.2 TB/s on a B200, the same kernel drawing its
+// tiles from an atomic ticket counter 6.85 TB/s (tools/probes/copy_patterns.cu,
+// profiles/r02_copy_patterns.txt): SMs do not all stream at the same speed (two dies, far and near L2
+// slices), and with a static split the launch lasts as long as its slowest SM.  So the ring draws its
+// tiles: whoever refills a stage takes the next ticket, writes the tile number next to the stage and
+// issues the bulk copy; consumers learn the tile from there.  A ticket past the last tile is recorded
+// as kNoTile and completes the stage's barrier without a copy -- the CTA's cue to leave.
+// `tickets` = {next tile, CTAs finished}: context-owned, zero between launches, re-armed by the last
+// CTA to finish (finish()).
+constexpr uint64_t kNoTile = ~0ull;
+
+template <int kTileBytes, int kStages, int kPadBytes = 16, bool kDynamic = true>
 struct TileRing {
     static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
     static constexpr int kStageBytes = kTileBytes + kPadBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kStages * 8 + kStages * 4 + 16;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStages * 8 + kStages * 8 + 24 + kStages * 4 + 16;
     static_assert(kStageBytes % 16 == 0, "stage base must stay 16-byte aligned");
 
     uint8_t* base;
     uint64_t* full;
+    uint64_t* tile_of;    // per stage: the tile it holds (or will hold), kNoTile past the end
+    uint64_t* hand;       // hand[2]: the tickets drawn ahead for the next two refills (release_warp protocol)
     uint32_t* released;   // per stage: warps that have finished reading it (release_warp protocol)
+    uint64_t in_hand, in_hand2;  // the same for release(): registers of thread 0
+    // release_warp(): tickets this lane drew that are on their way to hand[0] / hand[1] (kNoTicket: none;
+    // tickets fit 32 bits: a tile is >= 2 KB)
+    static constexpr uint32_t kNoTicket = 0xFFFFFFFFu;
+    uint32_t pend_even, pend_odd;
     const uint8_t* src;
     uint64_t src_bytes;   // readable bytes of the packed column, rounded up to 16
     uint64_t num_tiles;
     uint64_t policy;
+    unsigned long long* tickets;
 
-    __device__ __forceinline__ TileRing(uint8_t* smem, const void* packed, uint64_t readable_bytes16)
+    __device__ __forceinline__ TileRing(uint8_t* smem, const void* packed, uint64_t readable_bytes16,
+                                        unsigned long long* tickets_)
         : base(smem), full(reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes)),
-          released(reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + kStages * 8)), src(static_cast<const uint8_t*>(packed)), src_bytes(readable_bytes16),
-          num_tiles((readable_bytes16 + kTileBytes - 1) / kTileBytes), policy(0)
+          tile_of(reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kStages * 8)),
+          hand(reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kStages * 16)),
+          released(reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + kStages * 16 + 24)), in_hand(0), in_hand2(0),
+          pend_even(kNoTicket), pend_odd(kNoTicket),
+          src(static_cast<const uint8_t*>(packed)), src_bytes(readable_bytes16),
+          num_tiles((readable_bytes16 + kTileBytes - 1) / kTileBytes), policy(0), tickets(tickets_)
     {
     }
 
@@ -148,14 +182,46 @@ struct TileRing {
         return reinterpret_cast<const uint32_t*>(base + stage * kStageBytes);
     }
 
-    // thread 0 only
-    __device__ __forceinline__ void issue(uint64_t tile, int stage)
+    // A ticket costs a round trip to L2 (~0.4 us), too much to sit between "stage free" and "copy issued"
+    // when a tile is worth a microsecond of work or less (11-13 KB scan tiles: 0.98 -> 0.83 of the peak
+    // with the draw inline; the K <= 8 shared scans -10..20 %).  So tickets are drawn AHEAD and nobody ever
+    // waits for one:
+    //   release()       thread 0 keeps the next two tickets in registers; the one it draws now is used two
+    //                   tiles later
+    //   release_warp()  the refilling lane takes the ticket from `hand` (shared memory), draws the next into
+    //                   a register and publishes it at the start of ITS next release_warp() -- a whole
+    //                   tile of work later, and always before the next refill can happen (the next stage
+    //                   is released only after every warp, this one included, has read it)
+    // kDynamic = false keeps round 1's static order (CTA b: tiles b, b + grid, ...; a per-CTA counter in
+    // shared memory stands in for the global one).  The K <= 8 shared-scan kernels are the one family that
+    // measured FASTER with it (8-20 %, profiles/r02_ab_static_k8.txt); -DSSS_RING_STATIC=1 forces it
+    // everywhere for A/B runs.
+#ifndef SSS_RING_STATIC
+#define SSS_RING_STATIC 0
+#endif
+    __device__ __forceinline__ uint64_t draw()
     {
-        const uint64_t off = tile * (uint64_t)kTileBytes;
-        const uint64_t left = src_bytes - off;
-        const uint32_t bytes = left < (uint64_t)kTileBytes ? (uint32_t)left : (uint32_t)kTileBytes;
-        mbar_arrive_expect_tx(&full[stage], bytes);
-        bulk_g2s(base + stage * kStageBytes, src + off, bytes, &full[stage], policy);
+        if constexpr (!kDynamic || SSS_RING_STATIC)
+            return blockIdx.x + (uint64_t)atomicAdd(reinterpret_cast<unsigned int*>(hand + 2), 1u) * gridDim.x;
+        else
+            return atomicAdd(tickets, 1ull);
+    }
+
+    // one thread: start the copy of `tile` into `stage` (or record the end)
+    __device__ __forceinline__ void fill(int stage, uint64_t tile)
+    {
+        if (tile < num_tiles) {
+            tile_of[stage] = tile;
+            const uint64_t off = tile * (uint64_t)kTileBytes;
+            const uint64_t left = src_bytes - off;
+            const uint32_t bytes = left < (uint64_t)kTileBytes ? (uint32_t)left : (uint32_t)kTileBytes;
+            if (policy == 0) policy = l2_policy_evict_first();
+            mbar_arrive_expect_tx(&full[stage], bytes);
+            bulk_g2s(base + stage * kStageBytes, src + off, bytes, &full[stage], policy);
+        } else {
+            tile_of[stage] = kNoTile;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
+        }
     }
 
     // all threads; returns after the barriers are initialised and the first kStages copies are issued
@@ -166,29 +232,54 @@ struct TileRing {
                 mbar_init(&full[s], 1);
                 released[s] = 0;
             }
+            hand[2] = 0;  // (the static order's per-CTA tile counter)
             fence_mbar_init();
-            policy = l2_policy_evict_first();
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            uint64_t t = blockIdx.x;
-            for (int s = 0; s < kStages && t < num_tiles; s++, t += gridDim.x) issue(t, s);
+            uint64_t t[kStages + 2];
+#pragma unroll
+            for (int s = 0; s < kStages + 2; s++) t[s] = draw();  // independent atomics: one round trip for all
+#pragma unroll
+            for (int s = 0; s < kStages; s++) fill(s, t[s]);
+            in_hand = t[kStages];      // release():      the tickets of the next two refills (even / odd iter)
+            in_hand2 = t[kStages + 1];
+            hand[0] = t[kStages];      // release_warp(): the same two, refill i takes hand[i & 1]
+            hand[1] = t[kStages + 1];
         }
     }
 
-    __device__ __forceinline__ void wait(uint32_t iter)
+    // all threads: wait for the stage of iteration `iter`; returns the tile it holds, kNoTile = no more work
+    __device__ __forceinline__ uint64_t acquire(uint32_t iter)
     {
-        mbar_wait(&full[iter % kStages], (iter / kStages) & 1u);
+        const int stage = iter % kStages;
+        mbar_wait(&full[stage], (iter / kStages) & 1u);
+        return tile_of[stage];
     }
 
     // Barrier-free release for kernels that copy their part of the tile into registers first and
     // compute afterwards: every warp calls this once it has READ its words of the stage (pass one of
     // the loaded values as `dep` so the call cannot be scheduled above the loads).  The last of the
     // CTA's warps to arrive refills the stage itself; nobody waits for anybody.
-    __device__ __forceinline__ void release_warp(uint32_t iter, uint64_t tile, uint32_t dep)
+    __device__ __forceinline__ void release_warp(uint32_t iter, uint32_t dep)
     {
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
+            // the ticket this lane drew at its last refill of the same parity (two or more tiles ago): publish
+            // it now, before this warp's arrival can let anybody refill this parity's slot again
+            if (iter & 1u) {
+                if (pend_odd != kNoTicket) {
+                    *reinterpret_cast<volatile uint64_t*>(hand + 1) = pend_odd;
+                    pend_odd = kNoTicket;
+                    __threadfence_block();
+                }
+            } else {
+                if (pend_even != kNoTicket) {
+                    *reinterpret_cast<volatile uint64_t*>(hand) = pend_even;
+                    pend_even = kNoTicket;
+                    __threadfence_block();
+                }
+            }
             const int stage = iter % kStages;
             uint32_t old;
             // `dep` is an unused operand: it only forces the loads that produced it to have completed
@@ -198,25 +289,45 @@ struct TileRing {
                          : "memory");
             if (old == (blockDim.x >> 5) - 1) {
                 released[stage] = 0;  // next touched only after the refilled tile has landed
-                const uint64_t next = tile + (uint64_t)kStages * gridDim.x;
-                if (next < num_tiles) {
-                    fence_proxy_async();
-                    if (policy == 0) policy = l2_policy_evict_first();
-                    issue(next, stage);
+                fence_proxy_async();
+                const uint64_t tile = *reinterpret_cast<volatile uint64_t*>(hand + (iter & 1u));
+                fill(stage, tile);
+                if (tile < num_tiles) {  // (past the end the slot keeps its invalid ticket)
+                    if (iter & 1u) pend_odd = (uint32_t)draw();
+                    else pend_even = (uint32_t)draw();
                 }
             }
         }
     }
 
     // all threads, after the tile of iteration `iter` has been consumed
-    __device__ __forceinline__ void release(uint32_t iter, uint64_t tile)
+    __device__ __forceinline__ void release(uint32_t iter)
     {
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint64_t next = tile + (uint64_t)kStages * gridDim.x;
-            if (next < num_tiles) {
-                fence_proxy_async();
-                issue(next, iter % kStages);
+            fence_proxy_async();
+            // two tickets in registers, one per parity of `iter`: the one drawn now is used two tiles later
+            if (iter & 1u) {
+                const uint64_t tile = in_hand2;
+                fill(iter % kStages, tile);
+                if (tile < num_tiles) in_hand2 = draw();
+            } else {
+                const uint64_t tile = in_hand;
+                fill(iter % kStages, tile);
+                if (tile < num_tiles) in_hand = draw();
+            }
+        }
+    }
+
+    // all threads, once, after the tile loop: the last CTA of the launch re-arms the ticket counter
+    __device__ __forceinline__ void finish()
+    {
+        __syncthreads();  // no warp of this CTA draws a ticket after this
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&tickets[1], 1ull) == gridDim.x - 1) {
+                tickets[0] = 0;
+                tickets[1] = 0;
             }
         }
     }

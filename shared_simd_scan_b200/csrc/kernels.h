@@ -10,10 +10,17 @@
 
 namespace sss {
 
+constexpr uint32_t kTicketSlots = 1024;  // launches in flight that may draw tiles concurrently
+
 struct Device {
     int ordinal;
     int sm_count;
     int smem_optin;  // max dynamic shared memory per CTA
+    // tile-ticket counters of the persistent kernels (common.cuh TileRing): kTicketSlots x {next tile,
+    // CTAs finished}, zero between launches (every launch re-arms its slot itself)
+    unsigned long long* ticket_pool = nullptr;
+    mutable uint32_t ticket_cursor = 0;
+    unsigned long long* next_tickets() const { return ticket_pool + 2 * (size_t)(ticket_cursor++ % kTicketSlots); }
 };
 
 // Where a kernel's match count goes: `result` (device, may be null = no count) is stored or added to by

@@ -143,13 +143,13 @@ template <int W, bool kSmem>
 __global__ void __launch_bounds__(kSThreads, 1)
 shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                                const uint8_t* __restrict__ g_index, int K, uint8_t* __restrict__ out,
-                               bool count_matches, const IndexSmemPlan plan)
+                               bool count_matches, const IndexSmemPlan plan, unsigned long long* __restrict__ tickets)
 {
     using Cfg = LinearCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
     const IntervalHist hist = hist_init(smem + Cfg::kRingBytes, plan);
     const PredIndexView ix = load_pred_index(g_index, smem + Cfg::kRingBytes + plan.hist_bytes, plan);
-    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    typename Cfg::Ring ring(smem, packed, readable_bytes16, tickets);
     ring.start();
 
     const uint64_t n_blocks = (n + 31) >> 5;
@@ -165,9 +165,9 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
     // rows read from global memory (through L1): my column of row 0
     const uint8_t* g_col = reinterpret_cast<const uint8_t*>(ix.masks) + 4 * my_col;
 
-    uint32_t iter = 0;
-    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
-        ring.wait(iter);
+    for (uint32_t iter = 0;; ++iter) {
+        const uint64_t tile = ring.acquire(iter);
+        if (tile == kNoTile) break;
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         uint32_t dep = 0;
         for (uint32_t b = 0; b < 32; b++) {
@@ -204,9 +204,9 @@ shared_scan_linear_wide_kernel(const void* __restrict__ packed, uint64_t readabl
                 }
             }
         }
-        ring.release_warp(iter, tile, dep);
+        ring.release_warp(iter, dep);
     }
-    __syncthreads();
+    ring.finish();
     if (count_matches) hist_flush(smem + Cfg::kRingBytes, plan, ix.num_bp, g_index);
 }
 
@@ -214,7 +214,8 @@ template <int W, bool kSmem>
 __global__ void __launch_bounds__(kSThreads, 1)
 shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                           const uint8_t* __restrict__ g_index, int K, uint8_t* __restrict__ out,
-                          unsigned long long* __restrict__ counts, bool count_matches, const IndexSmemPlan plan)
+                          unsigned long long* __restrict__ counts, bool count_matches, const IndexSmemPlan plan,
+                          unsigned long long* __restrict__ tickets)
 {
     using Cfg = LinearCfg<W>;
     using Rot = BlockRot<W, 8>;  // rotations by whole rows (8 codes) only
@@ -222,7 +223,7 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
     uint8_t* s_index = smem + Cfg::kRingBytes + plan.hist_bytes;
     const IntervalHist hist = hist_init(smem + Cfg::kRingBytes, plan);  // kSmem: empty, the rows carry the counters
     const PredIndexView ix = load_pred_index(g_index, s_index, plan);
-    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    typename Cfg::Ring ring(smem, packed, readable_bytes16, tickets);
     ring.start();
 
     const uint64_t n_blocks = (n + 31) >> 5;
@@ -235,9 +236,9 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
     const bool vec4 = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
     uint32_t direct[kDirectCountMaxK] = {};  // K <= 8: this thread's match counts
 
-    uint32_t iter = 0;
-    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
-        ring.wait(iter);
+    for (uint32_t iter = 0;; ++iter) {
+        const uint64_t tile = ring.acquire(iter);
+        if (tile == kNoTile) break;
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
         const bool active = gb < n_blocks;
@@ -249,7 +250,7 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
         uint32_t loaded = 0;
 #pragma unroll
         for (int k = 0; k < W; k++) loaded |= x[k];
-        ring.release_warp(iter, tile, loaded);  // the stage is free once every warp has copied its words
+        ring.release_warp(iter, loaded);  // the stage is free once every warp has copied its words
         if (active) {
             uint32_t id[32];
             if constexpr (kSmem) block_rows<W>(x, ix, id);  // row handles directly
@@ -357,7 +358,7 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
             }
         }
     }
-    __syncthreads();
+    ring.finish();  // (contains the __syncthreads that closes the counting)
     if (count_matches) {
         if (K <= kDirectCountMaxK) {
 #pragma unroll
@@ -394,7 +395,7 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
             configured_wide[dev.ordinal & 63] = smem;
         }
         shared_scan_linear_wide_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(
-            packed, readable, n, static_cast<const uint8_t*>(index), K, out, count_matches, plan);
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, count_matches, plan, dev.next_tickets());
         return cudaGetLastError();
     }
     static size_t configured[64] = {};
@@ -405,7 +406,7 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
         configured[dev.ordinal & 63] = smem;
     }
     shared_scan_linear_kernel<W, kSmem><<<grid, kSThreads, smem, stream>>>(
-        packed, readable, n, static_cast<const uint8_t*>(index), K, out, counts, count_matches, plan);
+        packed, readable, n, static_cast<const uint8_t*>(index), K, out, counts, count_matches, plan, dev.next_tickets());
     return cudaGetLastError();
 }
 

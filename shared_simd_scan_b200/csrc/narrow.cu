@@ -32,6 +32,16 @@ constexpr int kNThreads = 512;
 #define SSS_NARROW_CTAS 1  // CTAs per SM (2 measured no better: the kernel is bound by its 8 write streams)
 #endif
 constexpr int kNCtasPerSm = SSS_NARROW_CTAS;
+constexpr int kNStageBytes = (kNThreads / 32) * kSmallStageBytesPerWarp;  // the warps' wide-store stages (16 KB)
+// (measured: with at most 8 output streams the stores are not what limits these kernels, and the detour
+// through the stage costs 2-8 %: profiles/r02_ab_k8_wide.txt.  Off; -DSSS_NARROW_WIDE=1 rebuilds it.)
+#ifndef SSS_NARROW_WIDE
+#define SSS_NARROW_WIDE 0
+#endif
+static bool narrow_wide_ok(const void* out, uint64_t stride_words, bool linear)
+{
+    return SSS_NARROW_WIDE && !linear && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (stride_words & 3) == 0;
+}
 static_assert(kNarrowMaxK == kDirectCountMaxK, "the narrow path counts by popcount");
 
 template <int W>
@@ -46,7 +56,7 @@ struct NarrowCfg {
     static constexpr int kBlocksPerTile = kNThreads * kBT;
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
     static constexpr int kStages = 4;
-    using Ring = TileRing<kTileBytes, kStages>;
+    using Ring = TileRing<kTileBytes, kStages, 16, /*kDynamic=*/false>;  // static tile order: see common.cuh
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
     static_assert(kBits <= 13, "group index must stay small enough to replicate");
 };
@@ -54,7 +64,7 @@ struct NarrowCfg {
 inline int narrow_rep_log2(size_t ring_bytes, int entries)
 {
     int r = 5;
-    while (r > 0 && ring_bytes + ((size_t)entries * 4 << r) + 64 > (size_t)(224 / kNCtasPerSm - 4) * 1024) r--;
+    while (r > 0 && ring_bytes + ((size_t)entries * 4 << r) + kNStageBytes + 64 > (size_t)(224 / kNCtasPerSm - 4) * 1024) r--;
     return r;
 }
 
@@ -93,7 +103,8 @@ template <int W, bool kAll8>
 __global__ void __launch_bounds__(kNThreads, kNCtasPerSm)
 shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                           const uint8_t* __restrict__ g_index, int K_arg, void* __restrict__ out, uint64_t stride_words,
-                          bool linear, unsigned long long* __restrict__ counts, int rep_log2)
+                          bool linear, unsigned long long* __restrict__ counts, int rep_log2, bool wide,
+                          unsigned long long* __restrict__ tickets)
 {
     // kAll8: exactly 8 predicates (no per-predicate guards in the epilogue)
     const int K = kAll8 ? 8 : K_arg;
@@ -118,9 +129,12 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
         }
     }
     const uint32_t R = 1u << rep_log2;
+    // the warp's wide-store stage sits behind the table
+    uint32_t* const wstage = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes + (((size_t)Cfg::kEntries * 4) << rep_log2)) +
+                             (threadIdx.x >> 5) * (kSmallStageBytesPerWarp / 4);
     const uint32_t table_base = smem_u32(smem + Cfg::kRingBytes) + ((threadIdx.x & (R - 1)) << 2);
     const uint32_t table_stride = 4u << rep_log2;
-    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    typename Cfg::Ring ring(smem, packed, readable_bytes16, tickets);
     ring.start();  // contains the __syncthreads that publishes the table
 
     using Rot = BlockRot<W, 1>;
@@ -129,9 +143,9 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
     const uint32_t tail_bits = (uint32_t)(n & 31);
     uint32_t direct[kNarrowMaxK] = {};
 
-    uint32_t iter = 0;
-    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
-        ring.wait(iter);
+    for (uint32_t iter = 0;; ++iter) {
+        const uint64_t tile = ring.acquire(iter);
+        if (tile == kNoTile) break;
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         // thread t owns blocks t, t + 512, ... of the tile (lanes stay adjacent: conflict-free loads,
         // coalesced stores)
@@ -145,7 +159,7 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
 #pragma unroll
             for (int k = 0; k < W; k++) loaded |= x[u][k];
         }
-        ring.release_warp(iter, tile, loaded);
+        ring.release_warp(iter, loaded);
 #pragma unroll
         for (int u = 0; u < Cfg::kBT; u++) {
             const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + u * kNThreads + threadIdx.x;
@@ -185,8 +199,11 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
 #pragma unroll
             for (int k = 0; k < 8; k++)
                 if (kAll8 || k < K) direct[k] += __popc(r[k]);
+            const uint64_t gb_warp0 = gb - (threadIdx.x & 31);
             if (linear) {
                 store_block_small(static_cast<uint8_t*>(out) + gb * 4 * (uint64_t)K, r, K);
+            } else if (wide && gb_warp0 + 32 <= n_blocks) {  // warp-uniform: every lane has a block
+                store_words8_wide(wstage, r, K, static_cast<uint32_t*>(out) + gb_warp0, stride_words);
             } else {
                 uint32_t* p = static_cast<uint32_t*>(out) + gb;
 #pragma unroll
@@ -197,6 +214,7 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
             }
         }
     }
+    ring.finish();
     if (counts != nullptr) {
 #pragma unroll
         for (int k = 0; k < kNarrowMaxK; k++) {
@@ -232,14 +250,14 @@ struct FewCfg {
     static constexpr int kBlocksPerTile = kNThreads;  // one block per thread per tile
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
     static constexpr int kStages = kTileBytes >= 32 * 1024 ? 2 : 3;
-    using Ring = TileRing<kTileBytes, kStages>;
+    using Ring = TileRing<kTileBytes, kStages, 16, /*kDynamic=*/false>;  // static tile order: see common.cuh
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
     // lane-private replicas of the table from what the ring leaves over (compile-time: the index shift
     // below then folds into the code's extraction shift)
     static constexpr int rep_log2()
     {
         int r = 5;
-        while (r > 0 && kRingBytes + ((kBuckets * 4) << r) + 64 > 220 * 1024) r--;
+        while (r > 0 && kRingBytes + ((kBuckets * 4) << r) + kNStageBytes + 64 > 220 * 1024) r--;
         return r;
     }
     static constexpr int kRepLog2 = rep_log2();
@@ -342,7 +360,8 @@ template <int W, bool kAll8>
 __global__ void __launch_bounds__(kNThreads, 1)
 shared_scan_few_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                        const uint8_t* __restrict__ g_index, int K_arg, void* __restrict__ out, uint64_t stride_words,
-                       bool linear, unsigned long long* __restrict__ counts, const Pow2Table P)
+                       bool linear, unsigned long long* __restrict__ counts, const Pow2Table P, bool wide,
+                       unsigned long long* __restrict__ tickets)
 {
     // kAll8: exactly 8 predicates (no per-predicate guards in the epilogue)
     const int K = kAll8 ? 8 : K_arg;
@@ -367,8 +386,10 @@ shared_scan_few_kernel(const void* __restrict__ packed, uint64_t readable_bytes1
         }
     }
     const uint32_t table_base = smem_u32(smem + Cfg::kRingBytes);
+    uint32_t* const wstage = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes + Cfg::kTableBytes) +
+                             (threadIdx.x >> 5) * (kSmallStageBytesPerWarp / 4);
     const uint32_t lane_off = (threadIdx.x & ((1u << rep_log2) - 1u)) << 2;
-    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    typename Cfg::Ring ring(smem, packed, readable_bytes16, tickets);
     ring.start();  // contains the __syncthreads that publishes the table
 
     using Rot = BlockRot<W, 1>;
@@ -377,16 +398,16 @@ shared_scan_few_kernel(const void* __restrict__ packed, uint64_t readable_bytes1
     const uint32_t tail_bits = (uint32_t)(n & 31);
     uint32_t direct[kNarrowMaxK] = {};
 
-    uint32_t iter = 0;
-    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
-        ring.wait(iter);
+    for (uint32_t iter = 0;; ++iter) {
+        const uint64_t tile = ring.acquire(iter);
+        if (tile == kNoTile) break;
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         uint32_t x[W];
         load_block<W, 1>(buf, threadIdx.x, x, lane_rot);  // (W = 16, 24: rotated by lane_rot pieces, see BlockRot)
         uint32_t loaded = 0;
 #pragma unroll
         for (int k = 0; k < W; k++) loaded |= x[k];
-        ring.release_warp(iter, tile, loaded);
+        ring.release_warp(iter, loaded);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
         if (gb >= n_blocks) continue;
         const uint32_t keep = (tail_bits != 0 && gb == n_blocks - 1) ? ((1u << tail_bits) - 1u) : 0xFFFFFFFFu;
@@ -407,8 +428,11 @@ shared_scan_few_kernel(const void* __restrict__ packed, uint64_t readable_bytes1
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (kAll8 || k < K) direct[k] += __popc(r[k]);
+        const uint64_t gb_warp0 = gb - (threadIdx.x & 31);
         if (linear) {
             store_block_small(static_cast<uint8_t*>(out) + gb * 4 * (uint64_t)K, r, K);
+        } else if (wide && gb_warp0 + 32 <= n_blocks) {  // warp-uniform: every lane has a block
+            store_words8_wide(wstage, r, K, static_cast<uint32_t*>(out) + gb_warp0, stride_words);
         } else {
             uint32_t* p = static_cast<uint32_t*>(out) + gb;
 #pragma unroll
@@ -418,6 +442,7 @@ shared_scan_few_kernel(const void* __restrict__ packed, uint64_t readable_bytes1
             }
         }
     }
+    ring.finish();
     if (counts != nullptr) {
 #pragma unroll
         for (int k = 0; k < kNarrowMaxK; k++) {
@@ -432,7 +457,8 @@ static cudaError_t launch_few_w(const Device& dev, const void* packed, uint64_t 
                                 uint64_t stride_words, bool linear, unsigned long long* counts, cudaStream_t stream)
 {
     using Cfg = FewCfg<W>;
-    const size_t smem = Cfg::kRingBytes + Cfg::kTableBytes + 64;
+    const size_t smem = Cfg::kRingBytes + Cfg::kTableBytes + kNStageBytes + 64;
+    const bool wide = narrow_wide_ok(out, stride_words, linear);
     Pow2Table P;
     for (int k = 0; k < 32; k++) P.p[k] = 1u << k;
     static size_t configured[64] = {};
@@ -452,10 +478,12 @@ static cudaError_t launch_few_w(const Device& dev, const void* packed, uint64_t 
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     if (K == 8)
         shared_scan_few_kernel<W, true><<<grid, kNThreads, smem, stream>>>(
-            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, P);
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, P, wide,
+            dev.next_tickets());
     else
         shared_scan_few_kernel<W, false><<<grid, kNThreads, smem, stream>>>(
-            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, P);
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, P, wide,
+            dev.next_tickets());
     return cudaGetLastError();
 }
 
@@ -465,7 +493,8 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, c
 {
     using Cfg = NarrowCfg<W>;
     const int r = narrow_rep_log2(Cfg::kRingBytes, Cfg::kEntries);
-    const size_t smem = Cfg::kRingBytes + ((size_t)Cfg::kEntries * 4 << r) + 64;
+    const size_t smem = Cfg::kRingBytes + ((size_t)Cfg::kEntries * 4 << r) + kNStageBytes + 64;
+    const bool wide = narrow_wide_ok(out, stride_words, linear);
     static size_t configured[64] = {};
     if (configured[dev.ordinal & 63] < smem) {
         cudaError_t e = cudaFuncSetAttribute(shared_scan_narrow_kernel<W, true>,
@@ -483,10 +512,12 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, c
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     if (K == 8)
         shared_scan_narrow_kernel<W, true><<<grid, kNThreads, smem, stream>>>(
-            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, r);
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, r, wide,
+            dev.next_tickets());
     else
         shared_scan_narrow_kernel<W, false><<<grid, kNThreads, smem, stream>>>(
-            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, r);
+            packed, readable, n, static_cast<const uint8_t*>(index), K, out, stride_words, linear, counts, r, wide,
+            dev.next_tickets());
     return cudaGetLastError();
 }
 

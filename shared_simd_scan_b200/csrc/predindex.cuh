@@ -654,6 +654,32 @@ __device__ __forceinline__ void transpose32x8(const uint32_t (&m)[32], uint32_t 
     transpose_bits_32x8(r);
 }
 
+// ---- bitvector layout, up to 8 predicates: 128-bit stores through a warp-private stage --------------------
+// r[k] = the block's result word of predicate k.  Stored per thread that is one 32-bit word per
+// predicate (128 bytes per warp instruction); the SM moves far more bytes of 128-bit stores next to
+// the kernel's other traffic (shared.cu, "Wide stores").  The warp parks its 8 x 32 words in `stage`
+// (1 KB, conflict-free) and lane (k mod 4, q) writes words 4q..4q+3 of predicate k with one 128-bit
+// store: 2 store instructions per thread instead of 8.  All 32 lanes of the warp call this together;
+// `warp0` = bitvector 0's word of the warp's FIRST block; base and stride 16-byte aligned.
+constexpr int kSmallStageBytesPerWarp = 8 * 32 * 4;
+__device__ __forceinline__ void store_words8_wide(uint32_t* stage, const uint32_t (&r)[8], int K, uint32_t* warp0,
+                                                  uint64_t stride_words)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    __syncwarp();  // the previous block's wide reads of the stage are done
+#pragma unroll
+    for (int k = 0; k < 8; k++) stage[k * 32 + lane] = r[k];
+    __syncwarp();
+    const uint32_t kq = lane >> 3, q4 = (lane & 7) * 4;
+    uint32_t* pw = warp0 + (uint64_t)kq * stride_words + q4;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        if ((int)kq + 4 * i < K)
+            __stcs(reinterpret_cast<uint4*>(pw), *reinterpret_cast<const uint4*>(stage + (kq + 4 * i) * 32 + q4));
+        pw += 4 * stride_words;
+    }
+}
+
 // ---- linear layout, up to 8 predicates ----------------------------------------------------------------
 // 4 x 4 byte transpose: in a,b,c,d = four predicates' result words (byte g = codes 8g..8g+7);
 // out o[g] = bytes (a.g, b.g, c.g, d.g) = four consecutive predicate bytes of row g

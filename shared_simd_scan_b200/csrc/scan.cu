@@ -41,7 +41,7 @@ namespace sss {
 #define SSS_SCAN_ST(p, v) __stcs((p), (v))
 #endif
 
-enum ScanMode : int { kScalar = 0, kSwarLoTop0 = 1, kSwarLoTop1 = 2, kOneBit = 3 };
+enum ScanMode : int { kScalar = 0, kSwarLoTop0 = 1, kSwarLoTop1 = 2, kOneBit = 3, kBool2 = 4 };
 
 template <int W>
 struct ScanPlan {
@@ -52,8 +52,8 @@ struct ScanPlan {
     static constexpr int kG = !kVec ? 1 : (W == 1 ? 4 : (W % 4 == 0 ? 1 : (W % 2 == 0 ? 2 : 4)));
     static constexpr int kGroupWords = kG * W;
 #ifndef SSS_SCAN_TILE_WORDS
-#define SSS_SCAN_TILE_WORDS 16  // target words per thread per tile (x 1 KiB = tile bytes)
-#endif
+#define SSS_SCAN_TILE_WORDS 32  // target words per thread per tile (x 1 KiB = tile bytes).  16 in round 1; with
+#endif                          // tiles drawn from a ticket counter, tiles below ~20 KB (3, 6, 11-13 bit) lost 5-15 %
 #ifndef SSS_SCAN_MAX_CTAS
 #define SSS_SCAN_MAX_CTAS 2
 #endif
@@ -75,10 +75,22 @@ struct ScalarArgs {
 struct OneBitArgs {
     uint32_t flip, all;  // result = (x ^ flip) | all
 };
+// W = 2: the predicate is a boolean function of the code's two bits; m[v] = 0x55555555 if code value v
+// matches, else 0 (bit 2i of the result word = the predicate on field i)
+struct Bool2Args {
+    uint32_t m[4];
+};
+inline __host__ __device__ Bool2Args make_bool2(uint32_t lo, uint32_t hi)
+{
+    Bool2Args a;
+    for (uint32_t v = 0; v < 4; v++) a.m[v] = (lo <= v && v <= hi) ? 0x55555555u : 0u;
+    return a;
+}
 template <int W>
 struct ScanArgs {
     ScalarArgs scalar;
     OneBitArgs onebit;
+    Bool2Args bool2;
     std::conditional_t<(W >= 2 && W <= 16), SwarConsts<(W >= 2 && W <= 16) ? W : 2>, ScalarArgs> swar;
 };
 
@@ -102,6 +114,28 @@ __device__ __forceinline__ uint32_t eval_block(const uint32_t (&x)[W], const Sca
 {
     if constexpr (kMode == kOneBit) {
         return (x[0] ^ a.onebit.flip) | a.onebit.all;
+    } else if constexpr (kMode == kBool2) {
+        // Two-bit codes.  The word-parallel subtract chains of swar.cuh cost ~36 ALU-pipe instructions per
+        // 32 codes here -- at 2 bits the HBM roofline is 17 T codes/s and the kernel was ALU-bound at 0.85 of
+        // it.  A predicate on a 2-bit code is one of 16 boolean functions of (b1, b0): a two-level
+        // multiplexer over four launch-time masks evaluates it for the 16 fields of a word with 1 shift +
+        // 3 LOP3.  Word 0's results sit at the even bits; word 1's are added at the odd bits (one IMAD) and a
+        // three-stage inverse perfect shuffle + one byte permute bring code i to bit i.
+        static_assert(W == 2 || kMode != kBool2, "two-bit evaluator");
+        uint32_t r[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint32_t b0 = x[i % W], b1 = x[i % W] >> 1;
+            const uint32_t hi_half = (a.bool2.m[3] & b0) | (a.bool2.m[2] & ~b0);  // b1 = 1: values 3 / 2
+            const uint32_t lo_half = (a.bool2.m[1] & b0) | (a.bool2.m[0] & ~b0);  // b1 = 0: values 1 / 0
+            r[i] = (hi_half & b1) | (lo_half & ~b1);
+        }
+        uint32_t z = r[1] * 2u + r[0];  // (disjoint bits: the add is an OR, issued on the FMA pipe)
+        uint32_t u;
+        u = (z ^ (z >> 1)) & 0x22222222u; z = z ^ u ^ (u << 1);
+        u = (z ^ (z >> 2)) & 0x0C0C0C0Cu; z = z ^ u ^ (u << 2);
+        u = (z ^ (z >> 4)) & 0x00F000F0u; z = z ^ u ^ (u << 4);
+        return __byte_perm(z, 0u, 0x3120);  // the 8-bit stage of the shuffle swaps bytes 1 and 2
     } else if constexpr (kMode == kScalar) {
         return EvalBlock<W, 0>::run(x, a.scalar.lo_al, a.scalar.span_al);
     } else {
@@ -204,9 +238,9 @@ __device__ __forceinline__ uint32_t scan_tiles(typename ScanPlan<W>::Ring& ring,
     const uint32_t rot = rot_chunks<W>();
     uint32_t hits = 0;
 
-    uint32_t iter = 0;
-    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
-        ring.wait(iter);
+    for (uint32_t iter = 0;; ++iter) {
+        const uint64_t tile = ring.acquire(iter);
+        if (tile == kNoTile) break;
         const uint32_t* buf = ring.stage_words(iter % P::kStages);
         const uint64_t tile_block0 = tile * (uint64_t)P::kBlocksPerTile;
         uint32_t* tile_out = bitvec + tile_block0;
@@ -215,8 +249,9 @@ __device__ __forceinline__ uint32_t scan_tiles(typename ScanPlan<W>::Ring& ring,
         } else {
             hits += scan_tile<W, kMode, true>(buf, args, rot, tile_out, n_blocks - tile_block0, tail_bits);
         }
-        ring.release(iter, tile);
+        ring.release(iter);
     }
+    ring.finish();
     return hits;
 }
 
@@ -225,11 +260,11 @@ __global__ void __launch_bounds__(kThreads, ScanPlan<W>::kCtasPerSm)
 scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                   const __grid_constant__ ScanArgs<W> args, uint32_t* __restrict__ bitvec,
                   unsigned long long* __restrict__ count, unsigned long long* __restrict__ count_slot,
-                  bool accumulate)
+                  bool accumulate, unsigned long long* __restrict__ tickets)
 {
     using P = ScanPlan<W>;
     extern __shared__ __align__(128) uint8_t smem[];
-    typename P::Ring ring(smem, packed, readable_bytes16);
+    typename P::Ring ring(smem, packed, readable_bytes16, tickets);
     ring.start();
     const uint32_t hits = scan_tiles<W, kMode>(ring, args, n, bitvec);
     if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
@@ -274,7 +309,8 @@ __global__ void __launch_bounds__(kThreads, ScanPlan<W>::kCtasPerSm)
 scan_range_dev_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                       const uint32_t* __restrict__ d_lo, const uint32_t* __restrict__ d_hi,
                       uint32_t* __restrict__ bitvec, unsigned long long* __restrict__ count,
-                      unsigned long long* __restrict__ count_slot, bool accumulate)
+                      unsigned long long* __restrict__ count_slot, bool accumulate,
+                      unsigned long long* __restrict__ tickets)
 {
     using P = ScanPlan<W>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -287,13 +323,16 @@ scan_range_dev_kernel(const void* __restrict__ packed, uint64_t readable_bytes16
             bitvec[i] = 0u;
     } else {
         if (hi > code_mask(W)) hi = code_mask(W);
-        typename P::Ring ring(smem, packed, readable_bytes16);
+        typename P::Ring ring(smem, packed, readable_bytes16, tickets);
         ring.start();
         ScanArgs<W> args{};
         if constexpr (W == 1) {
             args.onebit.flip = (lo == 0 && hi == 0) ? 0xFFFFFFFFu : 0u;
             args.onebit.all = (lo == 0 && hi == 1) ? 0xFFFFFFFFu : 0u;
             hits = scan_tiles<W, kOneBit>(ring, args, n, bitvec);
+        } else if constexpr (W == 2) {
+            args.bool2 = make_bool2(lo, hi);
+            hits = scan_tiles<W, kBool2>(ring, args, n, bitvec);
         } else if constexpr (P::kSwar) {
             args.swar = make_swar_consts<W>(lo, hi);
             hits = args.swar.lo_top ? scan_tiles<W, kSwarLoTop1>(ring, args, n, bitvec)
@@ -336,7 +375,7 @@ static cudaError_t launch_mode(const Device& dev, const void* packed, uint64_t n
     const uint64_t max_ctas = (uint64_t)dev.sm_count * P::kCtasPerSm;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     scan_range_kernel<W, kMode><<<grid, kThreads, smem, stream>>>(packed, readable, n, args, bitvec, ct.result, ct.slot,
-                                                                  ct.accumulate);
+                                                                  ct.accumulate, dev.next_tickets());
     return cudaGetLastError();
 }
 
@@ -350,6 +389,9 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, u
         args.onebit.flip = (lo == 0 && hi == 0) ? 0xFFFFFFFFu : 0u;
         args.onebit.all = (lo == 0 && hi == 1) ? 0xFFFFFFFFu : 0u;
         return launch_mode<W, kOneBit>(dev, packed, n, args, bitvec, count, stream);
+    } else if constexpr (W == 2) {
+        args.bool2 = make_bool2(lo, hi);
+        return launch_mode<W, kBool2>(dev, packed, n, args, bitvec, count, stream);
     } else if constexpr (ScanPlan<W>::kSwar) {
         args.swar = make_swar_consts<W>(lo, hi);
         if (args.swar.lo_top) return launch_mode<W, kSwarLoTop1>(dev, packed, n, args, bitvec, count, stream);
@@ -380,7 +422,7 @@ static cudaError_t launch_w_dev(const Device& dev, const void* packed, uint64_t 
     const uint64_t max_ctas = (uint64_t)dev.sm_count * P::kCtasPerSm;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     scan_range_dev_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, d_lo, d_hi, bitvec, ct.result,
-                                                               ct.slot, ct.accumulate);
+                                                               ct.slot, ct.accumulate, dev.next_tickets());
     return cudaGetLastError();
 }
 

@@ -59,6 +59,16 @@ constexpr int kSThreads = SSS_SHARED_THREADS;
 #else
 #define SSS_ST(p, v) st_stream_u32((p), (v))
 #endif
+// the wide stores are PLAIN stores: with 64 and more output streams per CTA the evict-first hint of a
+// streaming store measured 1.5-3.5 % slower (profiles/r02_ab_plainst_wide.txt, 20-24 bit)
+#ifndef SSS_WIDE_STREAMING
+#define SSS_WIDE_STREAMING 0
+#endif
+#if SSS_WIDE_STREAMING
+#define SSS_ST4(p, v) __stcs((p), (v))
+#else
+#define SSS_ST4(p, v) (*(p) = (v))
+#endif
 
 template <int W>
 struct SharedCfg {
@@ -98,7 +108,8 @@ template <int W, bool kSmem, int kStage>
 __global__ void __launch_bounds__(kSThreads, 1)
 shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                    const uint8_t* __restrict__ g_index, int K, uint32_t* __restrict__ bitvecs, uint64_t stride_words,
-                   unsigned long long* __restrict__ counts, bool count_matches, const IndexSmemPlan plan)
+                   unsigned long long* __restrict__ counts, bool count_matches, const IndexSmemPlan plan,
+                   unsigned long long* __restrict__ tickets)
 {
     using Cfg = SharedCfg<W>;
     using Rot = BlockRot<W, 1>;
@@ -110,7 +121,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
     uint8_t* s_index = smem + kFront + plan.hist_bytes;
     const IntervalHist hist = hist_init(smem + kFront, plan);  // kSmem: empty, the rows carry the counters
     const PredIndexView ix = load_pred_index(g_index, s_index, plan);
-    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    typename Cfg::Ring ring(smem, packed, readable_bytes16, tickets);
     ring.start();  // contains the __syncthreads that publishes the index and the zeroed counters
 
     const uint64_t n_blocks = (n + 31) >> 5;
@@ -121,9 +132,9 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
     const uint32_t stride_bytes32 = (uint32_t)(stride_words * 4);
     uint32_t direct[kDirectCountMaxK] = {};  // K <= 8: this thread's match counts
 
-    uint32_t iter = 0;
-    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
-        ring.wait(iter);
+    for (uint32_t iter = 0;; ++iter) {
+        const uint64_t tile = ring.acquire(iter);
+        if (tile == kNoTile) break;
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t gb = tile * (uint64_t)Cfg::kBlocksPerTile + threadIdx.x;
         const bool active = gb < n_blocks;
@@ -135,7 +146,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
         uint32_t loaded = 0;
 #pragma unroll
         for (int k = 0; k < W; k++) loaded |= x[k];
-        ring.release_warp(iter, tile, loaded);  // the stage is free once every warp has copied its words
+        ring.release_warp(iter, loaded);  // the stage is free once every warp has copied its words
         // kWide: the warp exchanges its result words through shared memory, so lanes past the column's end
         // stay with their warp (their lookups run on whatever the tile holds -- every index stays inside the
         // tables --, they count nothing and store nothing)
@@ -240,7 +251,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
                     if (whole) {
 #pragma unroll
                         for (int i = 0; i < kStagePreds / 4; i++) {
-                            __stcs(reinterpret_cast<uint4*>(pw), *reinterpret_cast<const uint4*>(src + i * 128));
+                            SSS_ST4(reinterpret_cast<uint4*>(pw), *reinterpret_cast<const uint4*>(src + i * 128));
                             pw += 4 * stride_words;
                         }
                     } else {  // the last predicates of a ragged K, or the last warp of the column
@@ -249,7 +260,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
                             const uint4 v = *reinterpret_cast<const uint4*>(src + i * 128);
                             if (r0 + (int)kq + 4 * i < kk) {
                                 if (gbq + 4 <= n_blocks) {
-                                    __stcs(reinterpret_cast<uint4*>(pw), v);
+                                    SSS_ST4(reinterpret_cast<uint4*>(pw), v);
                                 } else {
                                     if (gbq + 0 < n_blocks) st_stream_u32(pw + 0, v.x);
                                     if (gbq + 1 < n_blocks) st_stream_u32(pw + 1, v.y);
@@ -292,7 +303,7 @@ shared_scan_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, u
             }
         }
     }
-    __syncthreads();
+    ring.finish();  // (contains the __syncthreads that closes the counting)
     if (count_matches) {
         if (K <= kDirectCountMaxK) {
 #pragma unroll
@@ -361,7 +372,8 @@ template <int W, bool kSmem>
 __global__ void __launch_bounds__(kWideThreads, 1)
 shared_scan_wide_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                         const uint8_t* __restrict__ g_index, int K, uint32_t* __restrict__ bitvecs,
-                        uint64_t stride_words, bool count_matches, const IndexSmemPlan plan)
+                        uint64_t stride_words, bool count_matches, const IndexSmemPlan plan,
+                        unsigned long long* __restrict__ tickets)
 {
     using Cfg = SharedWideCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -369,7 +381,7 @@ shared_scan_wide_kernel(const void* __restrict__ packed, uint64_t readable_bytes
     uint8_t* s_hist = smem + Cfg::kRingBytes + wide_stage_bytes(K);
     const IntervalHist hist = hist_init(s_hist, plan);
     const PredIndexView ix = load_pred_index(g_index, s_hist + plan.hist_bytes, plan);
-    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    typename Cfg::Ring ring(smem, packed, readable_bytes16, tickets);
     ring.start();
 
     const uint64_t n_blocks = (n + 31) >> 5;
@@ -379,9 +391,9 @@ shared_scan_wide_kernel(const void* __restrict__ packed, uint64_t readable_bytes
     const uint32_t rows_base = kSmem ? ix.rows_saddr : 0u;
     const uint32_t my_col = lane < cols ? lane : 0;  // lanes past the last column idle along
 
-    uint32_t iter = 0;
-    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
-        ring.wait(iter);
+    for (uint32_t iter = 0;; ++iter) {
+        const uint64_t tile = ring.acquire(iter);
+        if (tile == kNoTile) break;
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         uint32_t dep = 0;
         for (uint32_t step = 0; step < (uint32_t)Cfg::kSteps; step++) {
@@ -433,9 +445,9 @@ shared_scan_wide_kernel(const void* __restrict__ packed, uint64_t readable_bytes
             }
             __syncthreads();
         }
-        ring.release_warp(iter, tile, dep);
+        ring.release_warp(iter, dep);
     }
-    __syncthreads();
+    ring.finish();
     if (count_matches) hist_flush(s_hist, plan, ix.num_bp, g_index);
 }
 
@@ -459,7 +471,8 @@ static cudaError_t launch_wide(const Device& dev, const void* packed, uint64_t n
     const uint64_t max_ctas = (uint64_t)dev.sm_count;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     shared_scan_wide_kernel<W, kSmem><<<grid, kWideThreads, smem, stream>>>(
-        packed, readable, n, static_cast<const uint8_t*>(index), K, bitvecs, stride_words, count_matches, plan);
+        packed, readable, n, static_cast<const uint8_t*>(index), K, bitvecs, stride_words, count_matches, plan,
+        dev.next_tickets());
     return cudaGetLastError();
 }
 
@@ -483,7 +496,8 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
     const uint64_t max_ctas = (uint64_t)dev.sm_count;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     shared_scan_kernel<W, kSmem, kStage><<<grid, kSThreads, smem, stream>>>(
-        packed, readable, n, static_cast<const uint8_t*>(index), K, bitvecs, stride_words, counts, count_matches, plan);
+        packed, readable, n, static_cast<const uint8_t*>(index), K, bitvecs, stride_words, counts, count_matches, plan,
+        dev.next_tickets());
     return cudaGetLastError();
 }
 

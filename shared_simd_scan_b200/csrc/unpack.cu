@@ -36,17 +36,18 @@ struct UnpackCfg {
 #endif
 template <int W>
 __global__ void __launch_bounds__(kThreads, SSS_UNPACK_CTAS)
-unpack_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n, int32_t* __restrict__ out)
+unpack_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n, int32_t* __restrict__ out,
+              unsigned long long* __restrict__ tickets)
 {
     using Cfg = UnpackCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
-    typename Cfg::Ring ring(smem, packed, readable_bytes16);
+    typename Cfg::Ring ring(smem, packed, readable_bytes16, tickets);
     ring.start();
 
     constexpr uint32_t mask = code_mask(W);
-    uint32_t iter = 0;
-    for (uint64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++iter) {
-        ring.wait(iter);
+    for (uint32_t iter = 0;; ++iter) {
+        const uint64_t tile = ring.acquire(iter);
+        if (tile == kNoTile) break;
         const uint32_t* buf = ring.stage_words(iter % Cfg::kStages);
         const uint64_t tile_code0 = tile * (uint64_t)Cfg::kCodesPerTile;
 #pragma unroll
@@ -75,8 +76,9 @@ unpack_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64
                 }
             }
         }
-        ring.release(iter, tile);
+        ring.release(iter);
     }
+    ring.finish();
 }
 
 template <int W>
@@ -94,7 +96,7 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, i
     const uint64_t tiles = (readable + Cfg::kTileBytes - 1) / Cfg::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * SSS_UNPACK_CTAS;
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    unpack_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, out);
+    unpack_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, out, dev.next_tickets());
     return cudaGetLastError();
 }
 
