@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
             "(or `make -C shared_simd_scan_b200/csrc`). shared_simd_scan_b200 has no CPU fallback.")
     L = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("SSS_LIB_PATH") and not hasattr(L, name):
+            continue  # developer override: an older experimental build may lack the newest entry points
         fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args

@@ -146,17 +146,22 @@ template <int kTileBytes, int kStages, int kPadBytes = 16, bool kDynamic = true>
 struct TileRing {
     static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
     static constexpr int kStageBytes = kTileBytes + kPadBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kStages * 8 + kStages * 8 + 24 + kStages * 4 + 16;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStages * 8 + kStages * 8 + kStages * 8 + 16;
     static_assert(kStageBytes % 16 == 0, "stage base must stay 16-byte aligned");
 
     uint8_t* base;
     uint64_t* full;
     uint64_t* tile_of;    // per stage: the tile it holds (or will hold), kNoTile past the end
-    uint64_t* hand;       // hand[2]: the tickets drawn ahead for the next two refills (release_warp protocol)
-    uint32_t* released;   // per stage: warps that have finished reading it (release_warp protocol)
+    // per stage (release_warp protocol): low kCountBits = warps that have finished reading it, the bits above =
+    // the ticket for its refill, delivered by the arrival of the lane that drew it (26 bits: 64 M tiles; the
+    // launchers' columns stay far below -- a tile is at least 8 KB)
+    static constexpr int kCountBits = 6;
+    static constexpr uint32_t kTicketMask = (1u << (32 - kCountBits)) - 1u;
+    uint32_t* released;
+    static __device__ __forceinline__ uint32_t clamp_ticket(uint64_t t) { return t < kTicketMask ? (uint32_t)t : kTicketMask; }
     uint64_t in_hand, in_hand2;  // the same for release(): registers of thread 0
-    // release_warp(): tickets this lane drew that are on their way to hand[0] / hand[1] (kNoTicket: none;
-    // tickets fit 32 bits: a tile is >= 2 KB)
+    // release_warp(): tickets this lane drew and will hand on with its next even / odd arrival (kNoTicket:
+    // none; tickets fit 32 bits: a tile is >= 2 KB)
     static constexpr uint32_t kNoTicket = 0xFFFFFFFFu;
     uint32_t pend_even, pend_odd;
     const uint8_t* src;
@@ -169,8 +174,7 @@ struct TileRing {
                                         unsigned long long* tickets_)
         : base(smem), full(reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes)),
           tile_of(reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kStages * 8)),
-          hand(reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kStages * 16)),
-          released(reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + kStages * 16 + 24)), in_hand(0), in_hand2(0),
+          released(reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + kStages * 16)), in_hand(0), in_hand2(0),
           pend_even(kNoTicket), pend_odd(kNoTicket),
           src(static_cast<const uint8_t*>(packed)), src_bytes(readable_bytes16),
           num_tiles((readable_bytes16 + kTileBytes - 1) / kTileBytes), policy(0), tickets(tickets_)
@@ -188,29 +192,23 @@ struct TileRing {
     // waits for one:
     //   release()       thread 0 keeps the next two tickets in registers; the one it draws now is used two
     //                   tiles later
-    //   release_warp()  the refilling lane takes the ticket from `hand` (shared memory), draws the next into
-    //                   a register and publishes it at the start of ITS next release_warp() -- a whole
-    //                   tile of work later, and always before the next refill can happen (the next stage
-    //                   is released only after every warp, this one included, has read it)
-    // kDynamic = false keeps round 1's static order (CTA b: tiles b, b + grid, ...; a per-CTA counter in
-    // shared memory stands in for the global one).  The K <= 8 shared-scan kernels are the one family that
+    //   release_warp()  the refilling lane draws the next ticket of its parity into a register and hands it
+    //                   on with ITS arrival two tiles later (in the high half of the stage's arrival
+    //                   counter), where the last reader to arrive finds it
+    // kDynamic = false keeps round 1's static order (CTA b: tiles b, b + grid, ...: a stage's next tile
+    // follows from the one it held).  The K <= 8 shared-scan kernels are the one family that
     // measured FASTER with it (8-20 %, profiles/r02_ab_static_k8.txt); -DSSS_RING_STATIC=1 forces it
     // everywhere for A/B runs.
 #ifndef SSS_RING_STATIC
 #define SSS_RING_STATIC 0
 #endif
-    __device__ __forceinline__ uint64_t draw()
-    {
-        if constexpr (!kDynamic || SSS_RING_STATIC)
-            return blockIdx.x + (uint64_t)atomicAdd(reinterpret_cast<unsigned int*>(hand + 2), 1u) * gridDim.x;
-        else
-            return atomicAdd(tickets, 1ull);
-    }
+    __device__ __forceinline__ uint64_t draw() { return atomicAdd(tickets, 1ull); }
 
     // one thread: start the copy of `tile` into `stage` (or record the end)
     __device__ __forceinline__ void fill(int stage, uint64_t tile)
     {
-        if (tile < num_tiles) {
+        if (tile < num_tiles) {  // (static order past the end: kNoTile + k * grid wraps to a small number only after
+                                 //  2^64 tiles; tile_of is never kNoTile when a stage is released)
             tile_of[stage] = tile;
             const uint64_t off = tile * (uint64_t)kTileBytes;
             const uint64_t left = src_bytes - off;
@@ -232,11 +230,12 @@ struct TileRing {
                 mbar_init(&full[s], 1);
                 released[s] = 0;
             }
-            hand[2] = 0;  // (the static order's per-CTA tile counter)
             fence_mbar_init();
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && (!kDynamic || SSS_RING_STATIC)) {
+            for (int s = 0; s < kStages; s++) fill(s, blockIdx.x + (uint64_t)s * gridDim.x);
+        } else if (threadIdx.x == 0) {
             uint64_t t[kStages + 2];
 #pragma unroll
             for (int s = 0; s < kStages + 2; s++) t[s] = draw();  // independent atomics: one round trip for all
@@ -244,8 +243,8 @@ struct TileRing {
             for (int s = 0; s < kStages; s++) fill(s, t[s]);
             in_hand = t[kStages];      // release():      the tickets of the next two refills (even / odd iter)
             in_hand2 = t[kStages + 1];
-            hand[0] = t[kStages];      // release_warp(): the same two, refill i takes hand[i & 1]
-            hand[1] = t[kStages + 1];
+            pend_even = clamp_ticket(t[kStages]);      // release_warp(): the same two, carried by this lane's first arrivals
+            pend_odd = clamp_ticket(t[kStages + 1]);
         }
     }
 
@@ -264,37 +263,55 @@ struct TileRing {
     __device__ __forceinline__ void release_warp(uint32_t iter, uint32_t dep)
     {
         __syncwarp();
+        if constexpr (!kDynamic || SSS_RING_STATIC) {  // static order: the stage's next tile follows from the one it held
+            if ((threadIdx.x & 31) == 0) {
+                const int stage = iter % kStages;
+                uint32_t old;
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;  // after %3"
+                             : "=r"(old)
+                             : "r"(smem_u32(&released[stage])), "r"(1u), "r"(dep)
+                             : "memory");
+                if (old == (blockDim.x >> 5) - 1) {
+                    released[stage] = 0;
+                    fence_proxy_async();
+                    fill(stage, tile_of[stage] + (uint64_t)kStages * gridDim.x);
+                }
+            }
+            return;
+        }
         if ((threadIdx.x & 31) == 0) {
-            // the ticket this lane drew at its last refill of the same parity (two or more tiles ago): publish
-            // it now, before this warp's arrival can let anybody refill this parity's slot again
+            // This lane's arrival carries, in the counter's high half, the ticket it drew at its last refill
+            // of the same parity (two tiles ago or more) -- so the ticket reaches the next refiller through
+            // the arrival atomic itself: no second shared-memory location, no fence.  (A first version
+            // published it with a store + __threadfence_block: the fence waits for the lane's outstanding
+            // global stores and cost the K <= 8 kernels 10 %.)
+            uint32_t add = 1u;
             if (iter & 1u) {
-                if (pend_odd != kNoTicket) {
-                    *reinterpret_cast<volatile uint64_t*>(hand + 1) = pend_odd;
-                    pend_odd = kNoTicket;
-                    __threadfence_block();
-                }
+                if (pend_odd != kNoTicket) add |= pend_odd << kCountBits;
+                pend_odd = kNoTicket;
             } else {
-                if (pend_even != kNoTicket) {
-                    *reinterpret_cast<volatile uint64_t*>(hand) = pend_even;
-                    pend_even = kNoTicket;
-                    __threadfence_block();
-                }
+                if (pend_even != kNoTicket) add |= pend_even << kCountBits;
+                pend_even = kNoTicket;
             }
             const int stage = iter % kStages;
             uint32_t old;
             // `dep` is an unused operand: it only forces the loads that produced it to have completed
             asm volatile("atom.shared.add.u32 %0, [%1], %2;  // after %3"
                          : "=r"(old)
-                         : "r"(smem_u32(&released[stage])), "r"(1u), "r"(dep)
+                         : "r"(smem_u32(&released[stage])), "r"(add), "r"(dep)
                          : "memory");
-            if (old == (blockDim.x >> 5) - 1) {
+            old += add;
+            if ((old & ((1u << kCountBits) - 1u)) == (blockDim.x >> 5)) {  // the last reader: refill with the ticket the arrivals carried
                 released[stage] = 0;  // next touched only after the refilled tile has landed
                 fence_proxy_async();
-                const uint64_t tile = *reinterpret_cast<volatile uint64_t*>(hand + (iter & 1u));
+                const uint64_t tile = old >> kCountBits;
                 fill(stage, tile);
-                if (tile < num_tiles) {  // (past the end the slot keeps its invalid ticket)
-                    if (iter & 1u) pend_odd = (uint32_t)draw();
-                    else pend_even = (uint32_t)draw();
+                if (tile < num_tiles) {
+                    if (iter & 1u) pend_odd = clamp_ticket(draw());
+                    else pend_even = clamp_ticket(draw());
+                } else {  // past the end: keep handing an invalid ticket on
+                    if (iter & 1u) pend_odd = kTicketMask;
+                    else pend_even = kTicketMask;
                 }
             }
         }
@@ -304,6 +321,13 @@ struct TileRing {
     __device__ __forceinline__ void release(uint32_t iter)
     {
         __syncthreads();
+        if constexpr (!kDynamic || SSS_RING_STATIC) {
+            if (threadIdx.x == 0) {
+                fence_proxy_async();
+                fill(iter % kStages, tile_of[iter % kStages] + (uint64_t)kStages * gridDim.x);
+            }
+            return;
+        }
         if (threadIdx.x == 0) {
             fence_proxy_async();
             // two tickets in registers, one per parity of `iter`: the one drawn now is used two tiles later

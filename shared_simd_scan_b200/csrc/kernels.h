@@ -20,6 +20,10 @@ struct Device {
     // CTAs finished}, zero between launches (every launch re-arms its slot itself)
     unsigned long long* ticket_pool = nullptr;
     mutable uint32_t ticket_cursor = 0;
+    // scan.cu: columns of at most this many tiles per resident CTA take the ring-less kernel (SSS_SCAN_DIRECT_TILES
+    // in the environment at sss_ctx_create overrides it; 0 = always the persistent ring kernel -- the parity
+    // tests run both)
+    uint32_t scan_direct_tiles = 8;
     unsigned long long* next_tickets() const { return ticket_pool + 2 * (size_t)(ticket_cursor++ % kTicketSlots); }
 };
 

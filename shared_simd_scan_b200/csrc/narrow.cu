@@ -202,7 +202,7 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
             const uint64_t gb_warp0 = gb - (threadIdx.x & 31);
             if (linear) {
                 store_block_small(static_cast<uint8_t*>(out) + gb * 4 * (uint64_t)K, r, K);
-            } else if (wide && gb_warp0 + 32 <= n_blocks) {  // warp-uniform: every lane has a block
+            } else if (SSS_NARROW_WIDE && wide && gb_warp0 + 32 <= n_blocks) {  // warp-uniform: every lane has a block
                 store_words8_wide(wstage, r, K, static_cast<uint32_t*>(out) + gb_warp0, stride_words);
             } else {
                 uint32_t* p = static_cast<uint32_t*>(out) + gb;
@@ -431,7 +431,7 @@ shared_scan_few_kernel(const void* __restrict__ packed, uint64_t readable_bytes1
         const uint64_t gb_warp0 = gb - (threadIdx.x & 31);
         if (linear) {
             store_block_small(static_cast<uint8_t*>(out) + gb * 4 * (uint64_t)K, r, K);
-        } else if (wide && gb_warp0 + 32 <= n_blocks) {  // warp-uniform: every lane has a block
+        } else if (SSS_NARROW_WIDE && wide && gb_warp0 + 32 <= n_blocks) {  // warp-uniform: every lane has a block
             store_words8_wide(wstage, r, K, static_cast<uint32_t*>(out) + gb_warp0, stride_words);
         } else {
             uint32_t* p = static_cast<uint32_t*>(out) + gb;

@@ -21,7 +21,7 @@
 
 namespace sss {
 
-constexpr int kPosRounds = 8;                                // words per lane per tile
+constexpr int kPosRounds = 8;                                // words per lane per tile (32 measured slower: 0.18 -> 0.22 ms at 0.1 % selectivity)
 constexpr int kPosTileWords = kThreads * kPosRounds;         // 2048 words = 65536 codes per tile
 constexpr int kPosWarpWords = 32 * kPosRounds;               // 256 words per warp
 constexpr int kPosStage = 1024;                              // positions per round and warp (32 words x 32 bits)

@@ -278,6 +278,7 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
 #ifndef SSS_SCAN_DIRECT_MAXW
 #define SSS_SCAN_DIRECT_MAXW 1
 #endif
+
 template <int W, int kMode>
 __global__ void __launch_bounds__(kThreads)
 scan_direct_kernel(const void* __restrict__ packed, uint64_t n, const __grid_constant__ ScanArgs<W> args,
@@ -365,14 +366,17 @@ static cudaError_t launch_mode(const Device& dev, const void* packed, uint64_t n
     const uint64_t n_blocks = (n + 31) / 32;
     const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
     const uint64_t tiles = (readable + P::kTileBytes - 1) / P::kTileBytes;
-    if constexpr (W <= SSS_SCAN_DIRECT_MAXW) {
-        if (tiles < (1ull << 31)) {
-            scan_direct_kernel<W, kMode><<<(unsigned)tiles, kThreads, 0, stream>>>(packed, n, args, bitvec, ct.result,
-                                                                                 ct.slot, ct.accumulate);
-            return cudaGetLastError();
-        }
-    }
     const uint64_t max_ctas = (uint64_t)dev.sm_count * P::kCtasPerSm;
+    // Short columns (BASELINE configs[0]: 2^24 codes = 1024 tiles, a 4 us kernel at the HBM roofline): the
+    // persistent ring's prologue -- tickets, first bulk copies, barrier round trips -- is then most of the
+    // launch, and a plain grid of one short-lived CTA per tile reading straight from global memory / L2
+    // starts working at once (cfg 1 in a CUDA graph: 9.1 -> see profiles/r02_bench extras `cfg1`).
+    const bool small = tiles <= (uint64_t)dev.scan_direct_tiles * max_ctas;
+    if ((W <= SSS_SCAN_DIRECT_MAXW || small) && tiles < (1ull << 31)) {
+        scan_direct_kernel<W, kMode><<<(unsigned)tiles, kThreads, 0, stream>>>(packed, n, args, bitvec, ct.result, ct.slot,
+                                                                             ct.accumulate);
+        return cudaGetLastError();
+    }
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     scan_range_kernel<W, kMode><<<grid, kThreads, smem, stream>>>(packed, readable, n, args, bitvec, ct.result, ct.slot,
                                                                   ct.accumulate, dev.next_tickets());

@@ -53,8 +53,30 @@ def test_unpack_matches_oracle(sss, w):
         assert (out.astype(np.uint32) == codes).all()
 
 
+@pytest.fixture(params=["direct", "ring"])
+def scan_path(request, sss):
+    """Short columns take the ring-less scan kernel, long ones the persistent TMA-ring kernel
+    (csrc/scan.cu launch_mode).  The oracle comparisons use short columns, so they run twice: with the
+    default context, and with one created under SSS_SCAN_DIRECT_TILES=0, which always takes the ring."""
+    if request.param == "direct":
+        yield sss
+        return
+    from shared_simd_scan_b200 import api
+    dev_id = torch.cuda.current_device()
+    old = api._contexts.get(dev_id)
+    os.environ["SSS_SCAN_DIRECT_TILES"] = "0"
+    try:
+        api._contexts[dev_id] = api.Context(dev_id)
+    finally:
+        del os.environ["SSS_SCAN_DIRECT_TILES"]
+    yield sss
+    api._contexts[dev_id].close()
+    api._contexts[dev_id] = old
+
+
 @pytest.mark.parametrize("w", ALL_W)
-def test_scan_matches_oracle(sss, w):
+def test_scan_matches_oracle(scan_path, w):
+    sss = scan_path
     m = (1 << w) - 1
     for n in SIZES:
         codes, packed = column(n, w, seed=200 + w)
