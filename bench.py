@@ -563,10 +563,17 @@ def run_ours(args):
 
     # ---- e2e: the host-buffer C-ABI calls (what include/simd_scan.hpp wraps), pinned host memory ----
     e2e_steps = max(1, args.e2e_steps)
+    # the host side of a rank lives next to its GPU while it copies: pinned buffers are first-touched on the
+    # GPU's NUMA node and no copy crosses the socket interconnect (matters from 4 ranks per box on); the
+    # CPU baseline further down gets every core back
+    affinity0 = os.sched_getaffinity(0)
+    host_cpus = api.bind_host_thread(local)
     e2e, e2e_counts = measure_e2e_scan(D, api, columns, n, e2e_steps)
+    e2e["host_cpus_per_rank"] = host_cpus
     if world == 1:
         assert e2e_counts == final_counts, "host-buffer path and device-resident path disagree on the match counts"
     e2e_shared = measure_e2e_shared(D, api, columns, n, e2e_steps) if not args.no_extras else None
+    os.sched_setaffinity(0, affinity0)
 
     # ---- the compact per-K summary, at every N (per-GPU device-resident numbers: max time over ranks) ----
     summary = {}

@@ -187,6 +187,13 @@ void* sss_host_alloc(size_t bytes); /* pinned host memory, NULL on failure */
 void sss_host_free(void* p);
 int sss_host_register(void* p, size_t bytes);
 int sss_host_unregister(void* p);
+/* Bind the CALLING host thread to the CPUs next to a GPU (its PCIe root's NUMA node, from
+ * /sys/bus/pci/devices/<bdf>/local_cpulist), so that the pinned buffers this thread allocates and
+ * first touches afterwards are node-local and its copies do not cross the socket interconnect.  On a
+ * one-node box, or where sysfs does not say, it changes nothing and returns SSS_OK; *n_cpus (may be
+ * NULL) = CPUs the thread may run on afterwards.  The multi-GPU host entry points call it for their
+ * per-GPU threads; a one-process-per-GPU launcher calls it once per rank (bench.py does). */
+int sss_bind_host_thread(int device, int* n_cpus);
 
 /* ---- multi-GPU entry points (the reference is single-device) --------
  * One process drives N GPUs.  The column is RANGE-partitioned: shard g holds codes

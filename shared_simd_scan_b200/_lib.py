@@ -63,6 +63,7 @@ SIGNATURES = {
     "sss_host_free": (None, [_vp]),
     "sss_host_register": (_i, [_vp, _sz]),
     "sss_host_unregister": (_i, [_vp]),
+    "sss_bind_host_thread": (_i, [_i, C.POINTER(_i)]),
 }
 
 

@@ -343,3 +343,11 @@ def host_shared_scan_into(packed: Host, n: int, w: int, lo: np.ndarray, hi: np.n
 def pinned_empty(nbytes: int) -> torch.Tensor:
     """Pinned host buffer (full-speed PCIe copies for the host_* operators)."""
     return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+
+
+def bind_host_thread(device: int) -> int:
+    """Bind the calling thread to the CPUs next to GPU `device` (sss_bind_host_thread): pinned buffers
+    allocated afterwards are node-local.  Returns the number of CPUs the thread may run on."""
+    n = C.c_int(0)
+    check(lib().sss_bind_host_thread(device, C.byref(n)), "sss_bind_host_thread")
+    return n.value

@@ -2,6 +2,8 @@
 // points, and the host-buffer entry points that the C++ drop-in layer (include/simd_scan.hpp)
 // calls.  Every CUDA return code is checked and surfaced as an int status; there is no CPU path.
 #include <cuda_runtime.h>
+#include <sched.h>
+#include <cctype>
 
 #include <algorithm>
 #include <cstdio>
@@ -867,6 +869,55 @@ void* sss_host_alloc(size_t bytes)
 void sss_host_free(void* p)
 {
     if (p) cudaFreeHost(p);
+}
+
+int sss_bind_host_thread(int device, int* n_cpus)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return SSS_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) return SSS_ERR_INVALID_ARG;
+    char bdf[32] = {0};
+    SSS_CK(cudaDeviceGetPCIBusId(bdf, sizeof bdf, device));
+    for (char* c = bdf; *c; c++) *c = (char)tolower(*c);
+    cpu_set_t now;
+    CPU_ZERO(&now);
+    sched_getaffinity(0, sizeof now, &now);
+    char path[128], list[4096] = {0};
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bdf);
+    if (FILE* f = fopen(path, "r")) {
+        const size_t k = fread(list, 1, sizeof list - 1, f);
+        list[k] = 0;
+        fclose(f);
+    }
+    // "0-15,32-47" -> the CPUs of that list this thread is allowed on already (a container's cpuset stays in force)
+    cpu_set_t want;
+    CPU_ZERO(&want);
+    int n = 0;
+    for (const char* p = list; *p && *p != '\n';) {
+        char* end = nullptr;
+        long a = strtol(p, &end, 10), b = a;
+        if (end == p) break;
+        p = end;
+        if (*p == '-') {
+            b = strtol(p + 1, &end, 10);
+            p = end;
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++)
+            if (CPU_ISSET(c, &now)) {
+                CPU_SET(c, &want);
+                n++;
+            }
+        if (*p == ',') p++;
+    }
+    if (n > 0 && sched_setaffinity(0, sizeof want, &want) == 0) {
+        if (n_cpus) *n_cpus = n;
+        return SSS_OK;
+    }
+    if (n_cpus) *n_cpus = CPU_COUNT(&now);
+    return SSS_OK;
 }
 
 int sss_host_register(void* p, size_t bytes) { return cuda_status(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); }

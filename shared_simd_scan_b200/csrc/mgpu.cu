@@ -258,6 +258,7 @@ int sss_mgpu_host_scan_range(sss_mgpu* m, const void* h_packed, uint64_t n, int 
     }
     for (int i = 0; i < m->n; i++) {
         team.emplace_back([&, i] {
+            sss_bind_host_thread(m->device[i], nullptr);  // this thread's staging buffers and copies stay next to its GPU
             uint64_t first, cnt;
             sss_shard_range(n, m->n, i, &first, &cnt);
             if (cnt == 0 && !(i == 0 && n == 0)) return;
@@ -298,6 +299,7 @@ int sss_mgpu_host_shared_scan(sss_mgpu* m, const void* h_packed, uint64_t n, int
     std::vector<std::thread> team;
     for (int i = 0; i < m->n; i++) {
         team.emplace_back([&, i] {
+            sss_bind_host_thread(m->device[i], nullptr);  // this thread's staging buffers and copies stay next to its GPU
             uint64_t first, cnt;
             sss_shard_range(n, m->n, i, &first, &cnt);
             if (cnt == 0) return;

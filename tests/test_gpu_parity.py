@@ -624,3 +624,27 @@ def test_positions_many_tiles_and_reuse(sss):
     bv, cnt = sss.scan(d_packed, n, w, 0, m // 2)
     pos, num = sss.positions(bv, n)
     assert (host(pos)[: int(num.item())].astype(np.uint64) == B.positions(exp, n)).all()
+
+
+@pytest.mark.parametrize("density", [0.0, 0.0005, 0.02, 0.3, 0.6, 1.0])
+def test_positions_every_density_and_unaligned_bitvector(sss, density):
+    """Position list of random bitvectors from empty to full (the staged path, the dense direct path and
+    rounds that switch between them), ragged sizes around the 1024-word segment, and a bitvector whose
+    address is only 4-byte aligned (sss_positions accepts that; the kernel then loads word by word)."""
+    rng = np.random.default_rng(int(density * 10_000) + 3)
+    for n in [1, 31, 33, 32767, 32768, 32769, 4096 * 32 + 5, (1 << 18) * 3 + 77]:
+        nbytes = (n + 7) // 8
+        bits = rng.random(nbytes * 8) < density
+        bv_h = np.packbits(bits.reshape(-1, 8)[:, ::-1], axis=1).reshape(-1)
+        # random garbage past bit n must be ignored
+        pad = rng.integers(0, 256, 64, dtype=np.uint8)
+        if n % 8:
+            bv_h[-1] |= np.uint8((0xFF << (n % 8)) & 0xFF)
+        exp = B.positions(np.concatenate([bv_h, pad]), n, base=11)
+        for off in (0, 4):
+            buf = torch.zeros(off + nbytes + 64 + 16, dtype=torch.uint8, device="cuda")
+            buf[off:off + nbytes + 64] = torch.from_numpy(np.concatenate([bv_h, pad])).cuda()
+            pos, num = sss.positions(buf[off:], n, base=11)
+            k = int(num.item())
+            assert k == len(exp), (n, density, off)
+            assert (host(pos)[:k].astype(np.uint64) == exp).all(), (n, density, off)
