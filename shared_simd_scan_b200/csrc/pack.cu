@@ -95,15 +95,24 @@ struct PackBlock<W, 32> {
 #ifndef SSS_PACK_WARPS
 #define SSS_PACK_WARPS 4
 #endif
-// Measured (tools/ab_pack.py): one short-lived CTA per 4 warp-rounds beats a grid capped at 12 CTAs per SM
-// by 10-30 %, and plain read-only loads beat evict-first streaming loads by 5-8 %.
-#ifndef SSS_PACK_CTAS_PER_SM
-#define SSS_PACK_CTAS_PER_SM (1u << 20)
-#endif
+// Measured (tools/ab_pack.py): short-lived CTAs beat a grid capped at 12 CTAs per SM by 10-30 %, and plain
+// read-only loads beat evict-first streaming loads by 5-8 %.
 #ifndef SSS_PACK_LOAD
 #define SSS_PACK_LOAD __ldg
 #endif
+// Rounds (of 1024 codes) a warp packs back to back.  The codes of round r+1 are requested BEFORE round r is
+// packed and written: with one round per warp the loads were outstanding for only ~40 % of a warp's life
+// (ncu: issue 30 %, 5.6-5.9 TB/s for a read-dominated kernel whose traffic mix streams at 6.8 TB/s).
+// Measured (profiles/r02_ab_pack_rounds.txt, fraction of the copy peak at 1 / 9 / 17 / 23 / 32 bit): one round
+// 1.03 / 0.88 / 0.88 / 0.89 / 0.91, two rounds 1.02 / 1.06 / 1.04 / 1.02 / 0.87, four 1.02 / 1.03 / 1.01 / 1.00 / 0.84.
+// At 32 bit the kernel is a copy (as many bytes written as read: the 1:1 mix tops out at 0.91) and stays
+// with one round.
+#ifndef SSS_PACK_ROUNDS
+#define SSS_PACK_ROUNDS 2
+#endif
 constexpr int kPackWarps = SSS_PACK_WARPS;  // 128-thread CTAs: 4 warps x (codes 4608 B + words <= 4224 B) of shared memory
+template <int W>
+constexpr int pack_rounds() { return W == 32 ? 1 : SSS_PACK_ROUNDS; }
 
 template <int W>
 __global__ void __launch_bounds__(kPackWarps * 32)
@@ -113,29 +122,48 @@ pack_block_kernel(const uint32_t* __restrict__ codes, uint64_t n_full_blocks, ui
     __shared__ __align__(16) uint4 s_codes[kPackWarps][32 * 9];  // [block][8 chunks + 1 pad]
     __shared__ uint32_t s_words[kPackWarps][32 * WP];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t warps_total = (uint64_t)gridDim.x * kPackWarps;
     const uint64_t groups = (n_full_blocks + 31) / 32;  // a warp packs 32 blocks = 1024 codes per round
-    for (uint64_t g = (uint64_t)blockIdx.x * kPackWarps + warp; g < groups; g += warps_total) {
+    constexpr int kPackRounds = pack_rounds<W>();
+    const uint64_t g0 = ((uint64_t)blockIdx.x * kPackWarps + warp) * kPackRounds;
+    if (g0 >= groups) return;
+    const uint32_t rounds = (uint32_t)((groups - g0) < (uint64_t)kPackRounds ? (groups - g0) : kPackRounds);
+
+    // chunk c = i*32 + lane of a round -> block c/8, slot c%8; nb = blocks of the round (32 but for the last)
+    auto blocks_of = [&](uint64_t g) {
         const uint64_t block0 = g * 32;
-        const uint32_t nb = (uint32_t)((n_full_blocks - block0) < 32 ? (n_full_blocks - block0) : 32);  // blocks here
-        const uint4* src = reinterpret_cast<const uint4*>(codes + block0 * 32);
-        // coalesced load of nb*8 chunks; chunk c -> block c/8, slot c%8
+        return (uint32_t)((n_full_blocks - block0) < 32 ? (n_full_blocks - block0) : 32);
+    };
+    auto request = [&](uint64_t g, uint4 (&v)[8]) {
+        const uint4* src = reinterpret_cast<const uint4*>(codes + g * 1024);
+        const uint32_t nb = blocks_of(g);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const uint32_t c = i * 32 + lane;
-            if (c < nb * 8) s_codes[warp][(c >> 3) * 9 + (c & 7)] = SSS_PACK_LOAD(src + c);
+            if (c < nb * 8) v[i] = SSS_PACK_LOAD(src + c);
+        }
+    };
+    uint4 v[8];
+    request(g0, v);
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint64_t g = g0 + r;
+        const uint32_t nb = blocks_of(g);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t c = i * 32 + lane;
+            if (c < nb * 8) s_codes[warp][(c >> 3) * 9 + (c & 7)] = v[i];
         }
         __syncwarp();
+        if (r + 1 < rounds) request(g + 1, v);  // in flight while this round is packed and written
         uint32_t out[W];
         if (lane < nb) {
             uint32_t cds[32];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                const uint4 v = s_codes[warp][lane * 9 + q];
-                cds[4 * q + 0] = v.x;
-                cds[4 * q + 1] = v.y;
-                cds[4 * q + 2] = v.z;
-                cds[4 * q + 3] = v.w;
+                const uint4 t = s_codes[warp][lane * 9 + q];
+                cds[4 * q + 0] = t.x;
+                cds[4 * q + 1] = t.y;
+                cds[4 * q + 2] = t.z;
+                cds[4 * q + 3] = t.w;
             }
             PackBlock<W, 0>::run(cds, out);
 #pragma unroll
@@ -143,11 +171,17 @@ pack_block_kernel(const uint32_t* __restrict__ codes, uint64_t n_full_blocks, ui
         }
         __syncwarp();
         // stream the nb*W words out, 128 bytes per warp store
-        uint32_t* dst = packed + block0 * W;
+        uint32_t* dst = packed + g * 32 * W;
         const uint32_t total = nb * W;
+        uint32_t b = lane / W, k = lane - b * W;  // word idx = b * W + k; idx += 32 per step
         for (uint32_t idx = lane; idx < total; idx += 32) {
-            const uint32_t b = idx / W, k = idx - b * W;
             __stcs(dst + idx, s_words[warp][b * WP + k]);
+            k += 32 % W;
+            b += 32 / W;
+            if (k >= (uint32_t)W) {
+                k -= W;
+                b++;
+            }
         }
         __syncwarp();
     }
@@ -157,11 +191,12 @@ template <int W>
 static cudaError_t launch_block_w(const Device& dev, const uint32_t* codes, uint64_t n_full_blocks, uint32_t* packed,
                                   cudaStream_t stream)
 {
+    (void)dev;
     const uint64_t groups = (n_full_blocks + 31) / 32;
-    const uint64_t want = (groups + kPackWarps - 1) / kPackWarps;
-    const uint64_t cap = std::min<uint64_t>((uint64_t)dev.sm_count * SSS_PACK_CTAS_PER_SM, 0x7FFFFFFFull);
-    const unsigned grid = (unsigned)(want < cap ? want : cap);
-    pack_block_kernel<W><<<grid, kPackWarps * 32, 0, stream>>>(codes, n_full_blocks, packed);
+    constexpr int kPackRounds = pack_rounds<W>();
+    const uint64_t want = (groups + (uint64_t)kPackWarps * kPackRounds - 1) / ((uint64_t)kPackWarps * kPackRounds);
+    if (want > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+    pack_block_kernel<W><<<(unsigned)want, kPackWarps * 32, 0, stream>>>(codes, n_full_blocks, packed);
     return cudaGetLastError();
 }
 
