@@ -112,7 +112,9 @@ struct PackBlock<W, 32> {
 #endif
 constexpr int kPackWarps = SSS_PACK_WARPS;  // 128-thread CTAs: 4 warps x (codes 4608 B + words <= 4224 B) of shared memory
 template <int W>
-constexpr int pack_rounds() { return W == 32 ? 1 : SSS_PACK_ROUNDS; }
+struct PackRounds {
+    static constexpr int value = W == 32 ? 1 : SSS_PACK_ROUNDS;
+};
 
 template <int W>
 __global__ void __launch_bounds__(kPackWarps * 32)
@@ -123,7 +125,7 @@ pack_block_kernel(const uint32_t* __restrict__ codes, uint64_t n_full_blocks, ui
     __shared__ uint32_t s_words[kPackWarps][32 * WP];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t groups = (n_full_blocks + 31) / 32;  // a warp packs 32 blocks = 1024 codes per round
-    constexpr int kPackRounds = pack_rounds<W>();
+    constexpr int kPackRounds = PackRounds<W>::value;
     const uint64_t g0 = ((uint64_t)blockIdx.x * kPackWarps + warp) * kPackRounds;
     if (g0 >= groups) return;
     const uint32_t rounds = (uint32_t)((groups - g0) < (uint64_t)kPackRounds ? (groups - g0) : kPackRounds);
@@ -193,7 +195,7 @@ static cudaError_t launch_block_w(const Device& dev, const uint32_t* codes, uint
 {
     (void)dev;
     const uint64_t groups = (n_full_blocks + 31) / 32;
-    constexpr int kPackRounds = pack_rounds<W>();
+    constexpr int kPackRounds = PackRounds<W>::value;
     const uint64_t want = (groups + (uint64_t)kPackWarps * kPackRounds - 1) / ((uint64_t)kPackWarps * kPackRounds);
     if (want > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
     pack_block_kernel<W><<<(unsigned)want, kPackWarps * 32, 0, stream>>>(codes, n_full_blocks, packed);
