@@ -43,10 +43,10 @@ constexpr int kPosSegWords = kPosRoundWords * kPosRounds;    // 1024 words = 327
 #endif
 constexpr int kPosStage = SSS_POS_STAGE;                              // positions a warp collects before it writes them out
 #ifndef SSS_POS_SPARSE
-#define SSS_POS_SPARSE 512
+#define SSS_POS_SPARSE 128
 #endif
 constexpr int kPosSparse = SSS_POS_SPARSE;                   // segments with at most this many set bits take the item path
-static_assert(kPosSparse * 6 <= kPosStage * 2, "the items (32-bit word + 16-bit index) live in the stage");
+static_assert(kPosRounds * 32 * 16 <= kPosStage * 2, "the items (a lane's 128-bit piece of a round) live in the stage");
 static_assert(kPosSegWords * 32 <= 65536, "stage entries are 16-bit offsets within the segment");
 
 static inline uint64_t pos_segments(uint64_t n)
@@ -166,7 +166,8 @@ pos_expand_kernel(const uint32_t* __restrict__ bitvec, uint64_t n, uint64_t segm
                   const uint32_t* __restrict__ seg_count, const unsigned long long* __restrict__ group_off, uint64_t base,
                   unsigned long long* __restrict__ positions, uint64_t capacity)
 {
-    __shared__ uint16_t stage[kWarps][kPosStage];
+    __shared__ __align__(16) uint16_t stage[kWarps][kPosStage];
+    __shared__ uint8_t piece_id[kWarps][kPosRounds * 32];
     const uint64_t n_words = (n + 31) >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -190,37 +191,36 @@ pos_expand_kernel(const uint32_t* __restrict__ bitvec, uint64_t n, uint64_t segm
 
     // Few bits set (at most kPosSparse in the segment, known from its count): the general path below
     // costs ~850 warp instructions per segment whatever it finds (32 per-word loops, four scans), which
-    // made the expansion issue-bound at 0.1-1 % selectivity (profiles/r02_ncu_pos_expand_sel001.txt).
-    // Here the non-zero WORDS are compacted first (four ballots per round place them in word order),
-    // then lane i expands item i: work follows the matches, not the words.
+    // made the expansion issue-bound at 0.1-1 % selectivity (profiles/r02_ncu_pos_expand_sel001_*.txt).
+    // Here the lanes' non-zero 128-bit pieces are compacted first (one ballot per round places them in
+    // word order; a segment has 256 pieces, so they always fit the stage), then lane i expands item i:
+    // work follows the matches, not the words.
     if (my_cnt <= (uint32_t)kPosSparse) {
-        uint32_t* item_word = reinterpret_cast<uint32_t*>(st);  // [kPosSparse]
-        uint16_t* item_idx = st + 2 * kPosSparse;               // [kPosSparse] word index within the segment
+        uint4* item_words = reinterpret_cast<uint4*>(st);  // [<= 256]
+        uint8_t* item_piece = piece_id[warp];              // [<= 256] round * 32 + lane
         const uint32_t lt = (1u << lane) - 1u;
         uint32_t items = 0;
 #pragma unroll
         for (int r = 0; r < kPosRounds; r++) {
-            const uint32_t x[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
-            uint32_t m[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) m[j] = __ballot_sync(0xFFFFFFFFu, x[j] != 0);
-            if ((m[0] | m[1] | m[2] | m[3]) == 0) continue;  // warp-uniform
-            uint32_t slot = items + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (x[j] != 0) {
-                    item_word[slot] = x[j];
-                    item_idx[slot] = (uint16_t)(r * kPosRoundWords + lane * 4 + j);
-                    slot++;
-                }
-            items += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+            const bool any = (v[r].x | v[r].y | v[r].z | v[r].w) != 0;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, any);
+            if (any) {
+                const uint32_t slot = items + __popc(m & lt);
+                item_words[slot] = v[r];
+                item_piece[slot] = (uint8_t)(r * 32 + lane);
+            }
+            items += __popc(m);
         }
         __syncwarp();
         for (uint32_t i0 = 0; i0 < items; i0 += 32) {
             const uint32_t i = i0 + lane;
-            uint32_t word = i < items ? item_word[i] : 0u;
-            const uint64_t code = seg_code0 + (i < items ? (uint32_t)item_idx[i] * 32u : 0u);
-            const uint32_t pc = __popc(word);
+            uint4 q = make_uint4(0, 0, 0, 0);
+            uint32_t piece = 0;
+            if (i < items) {
+                q = item_words[i];
+                piece = item_piece[i];
+            }
+            const uint32_t pc = popc4(q);
             uint32_t incl = pc;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -228,11 +228,17 @@ pos_expand_kernel(const uint32_t* __restrict__ bitvec, uint64_t n, uint64_t segm
                 if (lane >= (uint32_t)d) incl += t;
             }
             uint64_t dst = o + (incl - pc);
-            while (word) {
-                const int b = __ffs(word) - 1;
-                word &= word - 1;
-                if (dst < capacity) __stcs(positions + dst, code + b);
-                dst++;
+            const uint64_t code = seg_code0 + piece * 128u;  // piece = (round, lane): words 128 r + 4 lane .. + 3
+            const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t bits = x[j];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (dst < capacity) __stcs(positions + dst, code + j * 32 + b);
+                    dst++;
+                }
             }
             o += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
