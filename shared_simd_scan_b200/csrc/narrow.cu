@@ -55,7 +55,10 @@ struct NarrowCfg {
     static constexpr int kBT = 8 / W > 1 ? 8 / W : 1;
     static constexpr int kBlocksPerTile = kNThreads * kBT;
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
-    static constexpr int kStages = 4;
+#ifndef SSS_NARROW_STAGES_WIDE
+#define SSS_NARROW_STAGES_WIDE 3  // 11-13 bit: a shallower ring buys a doubling of the table replicas (11 bit 0.69 -> 0.82)
+#endif
+    static constexpr int kStages = W >= 11 ? SSS_NARROW_STAGES_WIDE : 4;
     using Ring = TileRing<kTileBytes, kStages, 16, /*kDynamic=*/false>;  // static tile order: see common.cuh
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
     static_assert(kBits <= 13, "group index must stay small enough to replicate");
@@ -249,7 +252,10 @@ template <int W>
 struct FewCfg {
     static constexpr int kBlocksPerTile = kNThreads;  // one block per thread per tile
     static constexpr int kTileBytes = kBlocksPerTile * W * 4;
-    static constexpr int kStages = kTileBytes >= 32 * 1024 ? 2 : 3;
+#ifndef SSS_FEW_TWO_STAGE_KB
+#define SSS_FEW_TWO_STAGE_KB 32
+#endif
+    static constexpr int kStages = kTileBytes >= SSS_FEW_TWO_STAGE_KB * 1024 ? 2 : 3;
     using Ring = TileRing<kTileBytes, kStages, 16, /*kDynamic=*/false>;  // static tile order: see common.cuh
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
     // lane-private replicas of the table from what the ring leaves over (compile-time: the index shift
