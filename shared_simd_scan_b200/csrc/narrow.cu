@@ -32,12 +32,13 @@ constexpr int kNThreads = 512;
 #define SSS_NARROW_CTAS 1  // CTAs per SM (2 measured no better: the kernel is bound by its 8 write streams)
 #endif
 constexpr int kNCtasPerSm = SSS_NARROW_CTAS;
-constexpr int kNStageBytes = (kNThreads / 32) * kSmallStageBytesPerWarp;  // the warps' wide-store stages (16 KB)
 // (measured: with at most 8 output streams the stores are not what limits these kernels, and the detour
 // through the stage costs 2-8 %: profiles/r02_ab_k8_wide.txt.  Off; -DSSS_NARROW_WIDE=1 rebuilds it.)
 #ifndef SSS_NARROW_WIDE
 #define SSS_NARROW_WIDE 0
 #endif
+// the warps' wide-store stages (16 KB) -- shared memory the table replicas get while the stage is off
+constexpr int kNStageBytes = SSS_NARROW_WIDE ? (kNThreads / 32) * kSmallStageBytesPerWarp : 0;
 static bool narrow_wide_ok(const void* out, uint64_t stride_words, bool linear)
 {
     return SSS_NARROW_WIDE && !linear && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (stride_words & 3) == 0;
@@ -50,6 +51,18 @@ struct NarrowCfg {
     static constexpr int kBits = kG * W;       // index bits
     static constexpr int kEntries = 1 << kBits;
     static constexpr int kLookups = 32 / kG;
+    // Byte tables (W >= kByteMinW, one code per lookup).  An entry of a one-code table is a single mask
+    // byte; kept as a 32-bit word it wastes three quarters of the shared memory that decides how many
+    // lane-private replicas fit -- and the replicas decide the bank conflicts of 32 random lookups
+    // (12 bit: 4 replicas, 2.6 wavefronts per lookup, 0.69 of the HBM peak; with three ring stages 8
+    // replicas and 0.73).  Packed four codes to the word the same memory holds four times the replicas
+    // (12 bit: 32, conflict-free; 13 bit: 16).  Replicas stay interleaved word by word, so a code's
+    // byte sits at ((code >> 2) * R + replica) * 4 + (code & 3): two more integer instructions per code.
+#ifndef SSS_NARROW_BYTE_MIN_W
+#define SSS_NARROW_BYTE_MIN_W 12
+#endif
+    static constexpr bool kByte = kG == 1 && W >= SSS_NARROW_BYTE_MIN_W;
+    static constexpr int kTableBytes = kByte ? kEntries : kEntries * 4;  // per replica
     // blocks per thread per tile: a block of narrow codes is only W words, and a tile has to be large
     // enough (>= 16 KB) for the ring's per-tile bookkeeping to disappear behind the work
     static constexpr int kBT = 8 / W > 1 ? 8 / W : 1;
@@ -64,10 +77,10 @@ struct NarrowCfg {
     static_assert(kBits <= 13, "group index must stay small enough to replicate");
 };
 
-inline int narrow_rep_log2(size_t ring_bytes, int entries)
+inline int narrow_rep_log2(size_t ring_bytes, int table_bytes)
 {
     int r = 5;
-    while (r > 0 && ring_bytes + ((size_t)entries * 4 << r) + kNStageBytes + 64 > (size_t)(224 / kNCtasPerSm - 4) * 1024) r--;
+    while (r > 0 && ring_bytes + ((size_t)table_bytes << r) + kNStageBytes + 64 > (size_t)(224 / kNCtasPerSm - 4) * 1024) r--;
     return r;
 }
 
@@ -90,7 +103,15 @@ struct GroupLookups {
     static __device__ __forceinline__ void run(const uint32_t (&x)[W], uint32_t base, uint32_t stride,
                                                uint32_t (&e)[NarrowCfg<W>::kLookups])
     {
-        asm("ld.shared.u32 %0, [%1];" : "=r"(e[G]) : "r"(group_index<W, G>(x) * stride + base));
+        if constexpr (NarrowCfg<W>::kByte) {
+            // byte of code v: word (v >> 2) of the lane's replica, byte v & 3.  v * stride / 4 puts the word
+            // offset right and drags the low two bits along, shifted: take those out, add them back unshifted
+            // (`unshift` = stride / 4 - 1).
+            const uint32_t v = group_index<W, G>(x);
+            asm("ld.shared.u8 %0, [%1];" : "=r"(e[G]) : "r"(v * (stride >> 2) + base - (v & 3u) * ((stride >> 2) - 1u)));
+        } else {
+            asm("ld.shared.u32 %0, [%1];" : "=r"(e[G]) : "r"(group_index<W, G>(x) * stride + base));
+        }
         GroupLookups<W, G + 1>::run(x, base, stride, e);
     }
 };
@@ -120,20 +141,25 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
         const uint32_t* masks = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kMasks);
         const uint32_t row_words = h->row_words;
         uint32_t* table = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);
-        for (uint32_t i = threadIdx.x; i < ((uint32_t)Cfg::kEntries << rep_log2); i += kNThreads) {
+        for (uint32_t i = threadIdx.x; i < ((uint32_t)(Cfg::kTableBytes / 4) << rep_log2); i += kNThreads) {
             const uint32_t v = i >> rep_log2;
             uint32_t entry = 0;
+            if constexpr (Cfg::kByte) {  // word v of a replica = the mask bytes of codes 4v .. 4v+3
 #pragma unroll
-            for (int c = 0; c < Cfg::kG; c++) {
-                const uint32_t code = (v >> (c * W)) & code_mask(W);
-                entry |= (masks[(uint32_t)lut[code] * row_words] & 0xFFu) << (8 * c);
+                for (int c = 0; c < 4; c++) entry |= (masks[(uint32_t)lut[4 * v + c] * row_words] & 0xFFu) << (8 * c);
+            } else {
+#pragma unroll
+                for (int c = 0; c < Cfg::kG; c++) {
+                    const uint32_t code = (v >> (c * W)) & code_mask(W);
+                    entry |= (masks[(uint32_t)lut[code] * row_words] & 0xFFu) << (8 * c);
+                }
             }
             table[i] = entry;
         }
     }
     const uint32_t R = 1u << rep_log2;
     // the warp's wide-store stage sits behind the table
-    uint32_t* const wstage = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes + (((size_t)Cfg::kEntries * 4) << rep_log2)) +
+    uint32_t* const wstage = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes + ((size_t)Cfg::kTableBytes << rep_log2)) +
                              (threadIdx.x >> 5) * (kSmallStageBytesPerWarp / 4);
     const uint32_t table_base = smem_u32(smem + Cfg::kRingBytes) + ((threadIdx.x & (R - 1)) << 2);
     const uint32_t table_stride = 4u << rep_log2;
@@ -498,8 +524,8 @@ static cudaError_t launch_w(const Device& dev, const void* packed, uint64_t n, c
                             uint64_t stride_words, bool linear, unsigned long long* counts, cudaStream_t stream)
 {
     using Cfg = NarrowCfg<W>;
-    const int r = narrow_rep_log2(Cfg::kRingBytes, Cfg::kEntries);
-    const size_t smem = Cfg::kRingBytes + ((size_t)Cfg::kEntries * 4 << r) + kNStageBytes + 64;
+    const int r = narrow_rep_log2(Cfg::kRingBytes, Cfg::kTableBytes);
+    const size_t smem = Cfg::kRingBytes + ((size_t)Cfg::kTableBytes << r) + kNStageBytes + 64;
     const bool wide = narrow_wide_ok(out, stride_words, linear);
     static size_t configured[64] = {};
     if (configured[dev.ordinal & 63] < smem) {
