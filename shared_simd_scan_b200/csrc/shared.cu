@@ -14,6 +14,7 @@
 //
 // Roofline: HBM.  Algorithmic bytes per code = W/8 + K/8.
 #include <array>
+#include <cstdlib>
 #include <utility>
 
 #include "common.cuh"
@@ -504,8 +505,16 @@ static cudaError_t launch_ws(const Device& dev, const void* packed, uint64_t n, 
 // Wide stores need every bitvector 16-byte aligned (base and stride) and at least one full column of
 // predicates; below 10 bits the kernel is closer to its instruction budget than to its store budget and
 // the narrow stores measured 1-2 % faster.
+//
+// OFF since the persistent CTAs draw their tiles from a ticket counter.  The wide stores were measured
+// and tuned under the static tile order (K = 64 at 17 bit: 0.72 -> 0.80).  With the dynamic order the
+// plain 32-bit stores -- one word per thread and predicate, no stage, no second trip through shared
+// memory -- are faster at EVERY width (profiles/r02_ab_wide_after_tickets.txt, K = 64: 10-13 bit 0.79 ->
+// 0.85, 17 bit 0.80 -> 0.86, 23 bit 0.85 -> 0.88, 28-32 bit 0.76-0.81 -> 0.88-0.91; K = 1024 +0-5 points):
+// CTAs no longer walk the 64 output streams in lockstep, which is what the narrow stores suffered from.
+// -DSSS_SHARED_WIDE=1 rebuilds the wide path (kept, parity-tested by tools/ab_variants.sh CHECK=1).
 #ifndef SSS_SHARED_WIDE
-#define SSS_SHARED_WIDE 1
+#define SSS_SHARED_WIDE 0
 #endif
 #ifndef SSS_WIDE_MIN_K
 #define SSS_WIDE_MIN_K 32
@@ -608,6 +617,13 @@ static constexpr auto make_group_table(std::integer_sequence<int, Ws...>)
 int shared_scan_predicate_group(int w, int K)
 {
     static constexpr auto table = make_group_table(std::make_integer_sequence<int, 32>{});
+    // developer switch: SSS_PRED_GROUP=<multiple of 32> forces the group size (A/B runs)
+    static const int forced = [] {
+        const char* e = std::getenv("SSS_PRED_GROUP");
+        const int g = e ? std::atoi(e) : 0;
+        return g >= 32 && g % 32 == 0 ? g : 0;
+    }();
+    if (forced && forced < K) return forced;
     return table[w - 1](K);
 }
 
