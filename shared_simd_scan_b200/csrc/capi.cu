@@ -182,7 +182,7 @@ int copy_threads()
 void par_memcpy(void* dst, const void* src, size_t bytes)
 {
     const int T = copy_threads();
-    if (T <= 1 || bytes < (4u << 20)) {
+    if (T <= 1 || bytes < (1u << 20)) {
         std::memcpy(dst, src, bytes);
         return;
     }
@@ -653,8 +653,11 @@ int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, u
     const size_t in_cap = round_up_u64(Ca / 32 * (uint64_t)w * 4, 16) + 16;
     SSS_CK(cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned long long), ctx->slots[0].stream));
     SSS_CK(cudaStreamSynchronize(ctx->slots[0].stream));
-    // (the bitvector is 1/8 byte per code: its pageable destination is served by the plain copy)
-    HostPipe pipe(ctx, is_pageable(h_packed), false);
+    // A pageable bitvector goes through the slot's bounce buffer too, small as it is: cudaMemcpyAsync into
+    // pageable memory returns only when the copy is done -- i.e. after the chunk's H2D copy and kernel --, which
+    // serialised the host's staging memcpy of chunk c+1 with the DMA of chunk c (16 GB/s whatever the
+    // number of copy threads, tools/pageable_probe.py).
+    HostPipe pipe(ctx, is_pageable(h_packed), is_pageable(h_bitvec));
     int slot = 0;
     for (uint64_t first = 0; first < n_eval; first += C, slot = (slot + 1) % kSlots) {
         Slot& s = ctx->slots[slot];
@@ -668,8 +671,11 @@ int sss_host_scan_range(sss_ctx* ctx, const void* h_packed, uint64_t n, int w, u
         SSS_TRY(scan_range_impl(ctx, s.d_in, cnt, w, lo, hi, s.d_out, ctx->d_counts, true, s.stream));
         const uint64_t out_off = first / 8;
         const uint64_t out_bytes = std::min<uint64_t>(4 * ((cnt + 31) / 32), out_total - out_off);
-        SSS_CK(cudaMemcpyAsync(static_cast<uint8_t*>(h_bitvec) + out_off, s.d_out, out_bytes, cudaMemcpyDeviceToHost,
-                               s.stream));
+        uint8_t* dst = static_cast<uint8_t*>(h_bitvec) + out_off;
+        if (pipe.out_staged())
+            SSS_TRY(pipe.copy_out_staged(slot, out_bytes, Ca / 8 + 16, {{dst, 0, (size_t)out_bytes}}));
+        else
+            SSS_CK(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
     }
     SSS_TRY(pipe.finish(slot));
     if (h_count) SSS_CK(cudaMemcpy(h_count, ctx->d_counts, sizeof(uint64_t), cudaMemcpyDeviceToHost));
