@@ -28,6 +28,8 @@
 namespace sss {
 
 constexpr int kNThreads = 512;
+constexpr int kNarrowTableMaxW = 15;                 // widest one-code table (32 KB of mask bytes per replica)
+constexpr uint64_t kNarrowTableMinN = 1ull << 24;    // ... used from this many codes on at 14 / 15 bit
 #ifndef SSS_NARROW_CTAS
 #define SSS_NARROW_CTAS 1  // CTAs per SM (2 measured no better: the kernel is bound by its 8 write streams)
 #endif
@@ -71,10 +73,10 @@ struct NarrowCfg {
 #ifndef SSS_NARROW_STAGES_WIDE
 #define SSS_NARROW_STAGES_WIDE 3  // 11-13 bit: a shallower ring buys a doubling of the table replicas (11 bit 0.69 -> 0.82)
 #endif
-    static constexpr int kStages = W >= 11 ? SSS_NARROW_STAGES_WIDE : 4;
+    static constexpr int kStages = W >= 15 ? 2 : (W >= 11 ? SSS_NARROW_STAGES_WIDE : 4);  // (15 bit: 4 replicas of 32 KB)
     using Ring = TileRing<kTileBytes, kStages, 16, /*kDynamic=*/false>;  // static tile order: see common.cuh
     static constexpr int kRingBytes = (Ring::kSmemBytes + 15) & ~15;
-    static_assert(kBits <= 13, "group index must stay small enough to replicate");
+    static_assert(kBits <= kNarrowTableMaxW, "group index must stay small enough to replicate");
 };
 
 inline int narrow_rep_log2(size_t ring_bytes, int table_bytes)
@@ -135,7 +137,37 @@ shared_scan_narrow_kernel(const void* __restrict__ packed, uint64_t readable_byt
     using Cfg = NarrowCfg<W>;
     extern __shared__ __align__(128) uint8_t smem[];
     // ---- prologue: the group table, `R` replicas interleaved entry by entry --------------------------
-    {
+    if constexpr (W > kDirectMaxW) {
+        // 14, 15 bit: the call's index locates codes through buckets, not directly.  With at most 8 predicates
+        // there are at most 16 breakpoints, so the byte table is filled from the index's thresholds: the mask
+        // of code c is the row of interval #{breakpoints <= c}.  One replica is computed (16 compares per
+        // code, 8-16 words per thread), the others are copies of it.
+        static_assert(Cfg::kByte, "wide one-code tables are byte tables");
+        __shared__ uint32_t s_thr[2 * kNarrowMaxK], s_mask[2 * kNarrowMaxK + 1];
+        const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(g_index + PredIndexLayout::kHeader);
+        const uint32_t* thr = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kThr);
+        const uint32_t* masks = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kMasks);
+        const uint32_t num_bp = h->num_bp, row_words = h->row_words;
+        if (threadIdx.x < 2 * kNarrowMaxK) s_thr[threadIdx.x] = threadIdx.x < num_bp ? thr[threadIdx.x] : 0xFFFFFFFFu;
+        if (threadIdx.x <= 2 * kNarrowMaxK) s_mask[threadIdx.x] = threadIdx.x <= num_bp ? masks[threadIdx.x * row_words] & 0xFFu : 0u;
+        __syncthreads();
+        uint32_t* table = reinterpret_cast<uint32_t*>(smem + Cfg::kRingBytes);
+        for (uint32_t v = threadIdx.x; v < (uint32_t)(Cfg::kTableBytes / 4); v += kNThreads) {
+            uint32_t entry = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t t = (4 * v + c) << (32 - W);  // left-aligned, like the thresholds
+                uint32_t id = 0;
+#pragma unroll
+                for (int k = 0; k < 2 * kNarrowMaxK; k++) id += t > s_thr[k] ? 1u : 0u;
+                entry |= s_mask[id] << (8 * c);
+            }
+            table[v << rep_log2] = entry;  // replica 0
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < ((uint32_t)(Cfg::kTableBytes / 4) << rep_log2); i += kNThreads)
+            if (i & ((1u << rep_log2) - 1u)) table[i] = table[i & ~((1u << rep_log2) - 1u)];
+    } else {
         const PredIndexHeader* h = reinterpret_cast<const PredIndexHeader*>(g_index + PredIndexLayout::kHeader);
         const uint16_t* lut = reinterpret_cast<const uint16_t*>(g_index + PredIndexLayout::kLocator);  // W <= 13: direct
         const uint32_t* masks = reinterpret_cast<const uint32_t*>(g_index + PredIndexLayout::kMasks);
@@ -573,6 +605,12 @@ cudaError_t launch_shared_scan_narrow(const Device& dev, const void* packed, uin
 {
     static constexpr auto table = make_table(std::make_integer_sequence<int, kNarrowMaxW>{});
     static constexpr auto few = make_few_table(std::make_integer_sequence<int, kFewMaxW - kNarrowMaxW>{});
+    // 14 and 15 bit: the one-code byte table (ten instructions per code instead of the bucket table's 16.5)
+    // once the column is long enough for its per-CTA table fill (~3 us) not to show
+    if (w == 14 && n >= kNarrowTableMinN)
+        return launch_w<14>(dev, packed, n, index, K, out, stride_words, linear, counts, stream);
+    if (w == 15 && n >= kNarrowTableMinN)
+        return launch_w<15>(dev, packed, n, index, K, out, stride_words, linear, counts, stream);
     if (w > kNarrowMaxW)
         return few[w - kNarrowMaxW - 1](dev, packed, n, index, K, out, stride_words, linear, counts, stream);
     return table[w - 1](dev, packed, n, index, K, out, stride_words, linear, counts, stream);

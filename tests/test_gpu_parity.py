@@ -648,3 +648,35 @@ def test_positions_every_density_and_unaligned_bitvector(sss, density):
             k = int(num.item())
             assert k == len(exp), (n, density, off)
             assert (host(pos)[:k].astype(np.uint64) == exp).all(), (n, density, off)
+
+
+@pytest.mark.parametrize("w", [14, 15])
+@pytest.mark.parametrize("K", [2, 5, 8])
+def test_one_code_byte_table_long_columns(sss, w, K):
+    """14 and 15 bit with K <= 8 switch from the bucket table to the one-code byte table (narrow.cu) once
+    the column has 2^24 codes; the short columns of the other tests never get there.  Breakpoints at 0-
+    and top-adjacent codes, equality, empty and full predicates, ragged length, both layouts, counts."""
+    n = (1 << 24) + 12_345
+    rng = np.random.default_rng(77 * w + K)
+    m = (1 << w) - 1
+    codes = rng.integers(0, m + 1, size=n, dtype=np.uint32)
+    codes[::7] = rng.integers(0, 9, size=len(codes[::7]), dtype=np.uint32)          # crowd the bottom of the domain
+    codes[3::7] = m - rng.integers(0, 9, size=len(codes[3::7]), dtype=np.uint32)    # ... and the top
+    packed = B.pack(codes, w)
+    lo = rng.integers(0, m + 1, size=K).astype(np.uint64)
+    hi = np.minimum(lo + rng.integers(0, (m + 1) // 4, size=K).astype(np.uint64), m)
+    lo[0], hi[0] = 1, 1                                  # equality right above 0
+    lo[1], hi[1] = 0, 3                                  # starts at 0: no breakpoint of its own below
+    if K > 2:
+        lo[2], hi[2] = m, m                              # the top code only
+        lo[3], hi[3] = 0, m                              # everything
+        lo[4], hi[4] = 9, 2                              # empty
+    exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
+    bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi)
+    nb = (n + 7) // 8
+    assert (host(bv)[:, :nb] == exp).all()
+    assert (host(cnt).astype(np.uint64) == ecnt).all()
+    lexp, lcnt = B.shared_scan_linear(packed, n, w, lo, hi, granule=1)
+    lin, cnt2 = sss.shared_scan_linear(dev(packed), n, w, lo, hi)
+    assert (host(lin)[: lexp.shape[0]] == lexp).all()
+    assert (host(cnt2).astype(np.uint64) == lcnt).all()
