@@ -24,6 +24,11 @@
 
 namespace sss {
 
+// developer switch: 0 = no row spreading (A/B runs; results stay correct)
+#ifndef SSS_LINEAR_SPREAD
+#define SSS_LINEAR_SPREAD 1
+#endif
+
 // Threads per CTA of the index-driven kernels: one 512-thread CTA per SM (see shared.cu).
 #ifndef SSS_SHARED_THREADS
 #define SSS_SHARED_THREADS 512
@@ -305,7 +310,7 @@ shared_scan_linear_kernel(const void* __restrict__ packed, uint64_t readable_byt
             constexpr int kLoadWays = Rot::kRot ? (Rot::kPieces >= 4 ? 4 : Rot::kPieces) : 1;  // rows the load rotation spreads over
             uint32_t extra = 0;
             if constexpr (kLoadWays < 4) {
-                extra = last ? 0u : ((threadIdx.x & 31u) & (uint32_t)(4 / kLoadWays - 1));
+                extra = (last || !SSS_LINEAR_SPREAD) ? 0u : ((threadIdx.x & 31u) & (uint32_t)(4 / kLoadWays - 1));
                 if (extra & 1u) {  // rotate by one row: position j takes the handle of position j + 8
                     uint32_t t[8];
 #pragma unroll
