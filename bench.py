@@ -813,7 +813,7 @@ def extras(args, api, columns, n, peak):
         b.synchronize()
         return a.elapsed_time(b) / reps
 
-    out = {"shared": [], "unpack": [], "pack": [], "positions": [], "calibration": calibration(api, timed, peak),
+    out = {"shared": [], "unpack": [], "pack": [], "positions": [], "scan_positions": [], "calibration": calibration(api, timed, peak),
            "cfg1": measure_cfg1(torch, api, peak)}
     out["e2e_pageable"] = measure_e2e_pageable(torch, api, columns, n)
     if not args.no_sweep:
@@ -853,7 +853,21 @@ def extras(args, api, columns, n, peak):
         out["positions"].append({"w": w, "n": n, "selectivity": sel, "hits": hits, "ms": round(ms, 4),
                                  "gcodes_per_s": round(n / ms / 1e6, 1), "gb_per_s": round(b / ms / 1e6, 1),
                                  "frac_of_measured_peak": round(b / ms / 1e6 / peak, 4)})
-        del pos_buf
+        # the north star's scan output in ONE call (sss_scan_range_positions): the scan fills the position
+        # list's segment counts itself, so the list costs group offsets + expansion, no count pass;
+        # bytes = packed column + bitvector written + 8 per match (the expansion's re-read is not counted)
+        bv2 = torch.empty_like(bv)
+        fused = lambda: api.scan_positions(columns[w], n, w, 0, hi_v, capacity=hits, out=bv2, pos_out=pos_buf,  # noqa: E731
+                                           count=cnt1)
+        ms_f = timed(fused, reps=5, warm=2)
+        ms_s = timed(lambda: api.scan(columns[w], n, w, 0, hi_v, out=bv2, count=cnt1), reps=5, warm=2)
+        assert int(cnt1.item()) == hits
+        bf = n * (w / 8 + 1 / 8) + 8.0 * hits
+        out["scan_positions"].append({"w": w, "n": n, "selectivity": sel, "hits": hits, "ms": round(ms_f, 4),
+                                      "ms_scan_alone": round(ms_s, 4), "ms_two_calls": round(ms_s + ms, 4),
+                                      "gcodes_per_s": round(n / ms_f / 1e6, 1), "gb_per_s": round(bf / ms_f / 1e6, 1),
+                                      "frac_of_measured_peak": round(bf / ms_f / 1e6 / peak, 4)})
+        del pos_buf, bv2
     del bv
     n2 = 1 << min(28, args.logn)
     dec = torch.empty(n2, dtype=torch.int32, device="cuda")

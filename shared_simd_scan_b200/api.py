@@ -167,7 +167,8 @@ def positions(bitvec: torch.Tensor, n: int, base: int = 0, capacity: Optional[in
 
 
 def scan_positions(packed: torch.Tensor, n: int, w: int, lo: int, hi: Optional[int] = None, base: int = 0,
-                   capacity: Optional[int] = None, out: Optional[torch.Tensor] = None
+                   capacity: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                   pos_out: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None
                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """The north star's scan output in one call: bitvector + match count + ascending position list
     (each position plus `base`) -> (bitvector, positions int64[capacity], count int64[1])."""
@@ -178,8 +179,11 @@ def scan_positions(packed: torch.Tensor, n: int, w: int, lo: int, hi: Optional[i
         out = torch.empty(bitvec_bytes(n), dtype=torch.uint8, device=packed.device)
     if capacity is None:
         capacity = n
-    pos = torch.empty(max(capacity, 1), dtype=torch.int64, device=packed.device)
-    count = torch.empty(1, dtype=torch.int64, device=packed.device)
+    pos = pos_out if pos_out is not None else torch.empty(max(capacity, 1), dtype=torch.int64, device=packed.device)
+    if pos.numel() < capacity:
+        raise ValueError("pos_out holds fewer than `capacity` positions")
+    if count is None:
+        count = torch.empty(1, dtype=torch.int64, device=packed.device)
     check(lib().sss_scan_range_positions(ctx.handle, packed.data_ptr(), n, w, lo & 0xFFFFFFFF, hi & 0xFFFFFFFF,
                                          out.data_ptr(), count.data_ptr(), base, pos.data_ptr(), capacity, _stream()),
           "sss_scan_range_positions")

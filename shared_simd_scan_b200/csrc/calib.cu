@@ -11,54 +11,72 @@
 //   mode COPY   : a -> b, `bytes` each way            (what MEASURED_PEAKS.json's hbm_gbs measures)
 //   mode MIX    : read `bytes` from a, write bytes/ratio to b: the traffic shape of scan_range_kernel<ratio>
 //
-// Plain grid-stride kernels with 128-bit accesses, 8 independent loads in flight per thread.
+// One CTA per contiguous CHUNK, 128-bit accesses, up to 8 independent loads in flight per thread.  The chunks
+// are handed out by the hardware CTA scheduler as SMs become free -- the same dynamic order the product
+// kernels get from their tile tickets.  (Until the end of round 2 these were grid-stride loops, i.e. a static
+// order, and undersold the hardware by 10-15 %: tools/probes/copy_patterns.cu measures 6.0-6.2 TB/s for a
+// grid-stride copy and 6.85 TB/s for the chunked one, profiles/r02_copy_patterns.txt.)
 #include "common.cuh"
 #include "kernels.h"
 
 namespace sss {
 
-constexpr int kCalibUnroll = 8;
+constexpr int kCalibUnroll = 8;   // READ / WRITE / COPY: vectors per thread and chunk (32 KB chunks)
+constexpr int kCalibMixOut = 2;   // MIX: output vectors per thread and chunk (8 KB out, ratio x 8 KB in)
 
 __global__ void __launch_bounds__(kThreads)
 calib_kernel(int mode, const uint4* __restrict__ a, uint4* __restrict__ b, uint64_t n_vec, uint32_t ratio,
              unsigned long long* __restrict__ sink)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
-    const uint64_t t0 = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
     uint32_t acc = 0;
-    if (mode == 1) {  // WRITE
-        const uint4 v = make_uint4((uint32_t)t0, 1u, 2u, 3u);
-        for (uint64_t i = t0; i < n_vec; i += stride) __stcs(b + i, v);
-    } else {
-        for (uint64_t base = t0; base < n_vec; base += stride * kCalibUnroll) {
+    if (mode == 3) {  // MIX: read ratio * kCalibMixOut vectors per thread, write kCalibMixOut
+        const uint64_t n_out = n_vec / ratio;
+        const uint64_t out0 = (uint64_t)blockIdx.x * (kThreads * kCalibMixOut);
+        const uint64_t in0 = out0 * ratio;
+        const uint32_t per_thread = ratio * kCalibMixOut;
+        for (uint32_t i0 = 0; i0 < per_thread; i0 += kCalibUnroll) {
             uint4 v[kCalibUnroll];
 #pragma unroll
             for (int u = 0; u < kCalibUnroll; u++) {
-                const uint64_t i = base + (uint64_t)u * stride;
-                v[u] = i < n_vec ? __ldcs(a + i) : make_uint4(0, 0, 0, 0);
+                const uint64_t i = in0 + (uint64_t)(i0 + u) * kThreads + threadIdx.x;
+                v[u] = (i0 + u < per_thread && i < n_vec) ? __ldcs(a + i) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
-            for (int u = 0; u < kCalibUnroll; u++) {
-                const uint64_t i = base + (uint64_t)u * stride;
-                if (mode == 2) {  // COPY
-                    if (i < n_vec) __stcs(b + i, v[u]);
-                } else {
-                    acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
-                }
-            }
-            if (mode == 3) {
-                // MIX: this round read kCalibUnroll * stride vectors CTA-wide; every `ratio`-th of them is
-                // written back, contiguously (thread t of the round writes vector base/ratio + ...)
-                const uint64_t round_first = base - t0;                  // first vector of the round
-                const uint64_t out_first = round_first / ratio;          // (rounds are multiples of ratio: see launch)
-                const uint64_t out_count = stride * kCalibUnroll / ratio;
-                const uint64_t n_out = n_vec / ratio;
-                for (uint64_t j = t0; j < out_count && out_first + j < n_out; j += stride)
-                    __stcs(b + out_first + j, make_uint4(acc, acc, acc, acc));
-            }
+            for (int u = 0; u < kCalibUnroll; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
         }
-        if (acc == 0x9E3779B9u && sink != nullptr) atomicAdd(sink, 1ull);  // keeps the loads alive
+#pragma unroll
+        for (int u = 0; u < kCalibMixOut; u++) {
+            const uint64_t o = out0 + (uint64_t)u * kThreads + threadIdx.x;
+            if (o < n_out) __stcs(b + o, make_uint4(acc, acc, acc, acc));
+        }
+        return;
     }
+    const uint64_t base = (uint64_t)blockIdx.x * (kThreads * kCalibUnroll) + threadIdx.x;
+    if (mode == 1) {  // WRITE
+        const uint4 v = make_uint4((uint32_t)base, 1u, 2u, 3u);
+#pragma unroll
+        for (int u = 0; u < kCalibUnroll; u++) {
+            const uint64_t i = base + (uint64_t)u * kThreads;
+            if (i < n_vec) __stcs(b + i, v);
+        }
+        return;
+    }
+    uint4 v[kCalibUnroll];
+#pragma unroll
+    for (int u = 0; u < kCalibUnroll; u++) {
+        const uint64_t i = base + (uint64_t)u * kThreads;
+        v[u] = i < n_vec ? __ldcs(a + i) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kCalibUnroll; u++) {
+        const uint64_t i = base + (uint64_t)u * kThreads;
+        if (mode == 2) {  // COPY
+            if (i < n_vec) __stcs(b + i, v[u]);
+        } else {
+            acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+        }
+    }
+    if (mode == 0 && acc == 0x9E3779B9u && sink != nullptr) atomicAdd(sink, 1ull);  // keeps the loads alive
 }
 
 // mode STREAMS32 / STREAMS128: the WRITE pattern of the shared scan's bitvector layout without any of
@@ -111,12 +129,12 @@ cudaError_t launch_calibrate(const Device& dev, int mode, const void* a, void* b
                                                                       stream_words, K);
         return cudaGetLastError();
     }
-    // grid: 8 CTAs per SM; for MIX the vectors a round covers must divide by the ratio -> round the grid
-    unsigned grid = (unsigned)dev.sm_count * 8;
-    if (mode == 3 && ratio > 1) grid = grid / ratio * ratio;
-    if (grid == 0) grid = ratio;
-    calib_kernel<<<grid, kThreads, 0, stream>>>(mode, static_cast<const uint4*>(a), static_cast<uint4*>(b), n_vec,
-                                                ratio == 0 ? 1 : ratio, sink);
+    const uint32_t r = ratio == 0 ? 1 : ratio;
+    const uint64_t per_cta = mode == 3 ? (uint64_t)kThreads * kCalibMixOut * r : (uint64_t)kThreads * kCalibUnroll;
+    const uint64_t ctas = (n_vec + per_cta - 1) / per_cta;
+    if (ctas >= (1ull << 31)) return cudaErrorInvalidValue;
+    calib_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(mode, static_cast<const uint4*>(a), static_cast<uint4*>(b), n_vec, r,
+                                                         sink);
     return cudaGetLastError();
 }
 

@@ -412,7 +412,8 @@ int sss_unpack(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, int32_t* d
 }
 
 static int scan_range_impl(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32_t lo, uint32_t hi,
-                           void* d_bitvec, unsigned long long* d_count, bool accumulate, cudaStream_t st)
+                           void* d_bitvec, unsigned long long* d_count, bool accumulate, cudaStream_t st,
+                           uint32_t* d_seg_count = nullptr)
 {
     const AlignedRange r = aligned_range(w, lo, hi);
     if (n == 0 || r.empty) {  // nothing can match: clear what a scan would have written
@@ -420,7 +421,7 @@ static int scan_range_impl(sss_ctx* ctx, const void* d_packed, uint64_t n, int w
         if (n != 0) SSS_CK(cudaMemsetAsync(d_bitvec, 0, 4 * ((n + 31) / 32), st));
         return SSS_OK;
     }
-    CountTarget ct{d_count, ctx->d_count_slots + 2 * (ctx->next_count_slot++ % kCountSlots), accumulate};
+    CountTarget ct{d_count, ctx->d_count_slots + 2 * (ctx->next_count_slot++ % kCountSlots), accumulate, d_seg_count};
     return cuda_status(launch_scan_range(ctx->dev, d_packed, n, w, r, static_cast<uint32_t*>(d_bitvec), ct, st));
 }
 
@@ -435,8 +436,7 @@ int sss_scan_range(sss_ctx* ctx, const void* d_packed, uint64_t n, int w, uint32
                            static_cast<cudaStream_t>(stream));
 }
 
-static int positions_impl(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base, uint64_t* d_positions,
-                          uint64_t capacity, uint64_t* d_num, cudaStream_t st)
+static int positions_workspace(sss_ctx* ctx, uint64_t n, cudaStream_t st)
 {
     const size_t need = positions_workspace_bytes(n);
     if (ctx->ws_cap < need || ctx->ws_epoch >= positions_epoch_limit()) {
@@ -446,9 +446,17 @@ static int positions_impl(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64
         SSS_CK(cudaMemsetAsync(ctx->d_ws, 0, ctx->ws_cap, st));
         ctx->ws_epoch = 0;
     }
+    return SSS_OK;
+}
+
+static int positions_impl(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base, uint64_t* d_positions,
+                          uint64_t capacity, uint64_t* d_num, cudaStream_t st, bool counted = false)
+{
+    SSS_TRY(positions_workspace(ctx, n, st));
     return cuda_status(launch_positions(ctx->dev, static_cast<const uint32_t*>(d_bitvec), n, base,
                                         reinterpret_cast<unsigned long long*>(d_positions), capacity,
-                                        reinterpret_cast<unsigned long long*>(d_num), ctx->d_ws, ++ctx->ws_epoch, st));
+                                        reinterpret_cast<unsigned long long*>(d_num), ctx->d_ws, ++ctx->ws_epoch, st,
+                                        counted));
 }
 
 int sss_positions(sss_ctx* ctx, const void* d_bitvec, uint64_t n, uint64_t base, uint64_t* d_positions,
@@ -471,10 +479,20 @@ int sss_scan_range_positions(sss_ctx* ctx, const void* d_packed, uint64_t n, int
     SSS_LOCK(ctx);
     SSS_CK(cudaSetDevice(ctx->dev.ordinal));
     auto st = static_cast<cudaStream_t>(stream);
-    // the scan writes the bitvector and the count; the position pass reads the bitvector while it is
-    // still (mostly) L2-resident and needs no count of its own
-    SSS_TRY(scan_range_impl(ctx, d_packed, n, w, lo, hi, d_bitvec, reinterpret_cast<unsigned long long*>(d_count), false, st));
-    return positions_impl(ctx, d_bitvec, n, base, d_positions, capacity, nullptr, st);
+    // The scan writes the bitvector, the count AND the matches of every 4 KB segment of the bitvector (one
+    // warp-aggregated atomic per warp and segment into the position workspace), so the position list starts
+    // at its second step: group offsets, then the ordered expansion, which reads the bitvector while it is
+    // still (mostly) L2-resident.  An empty predicate writes zeros without a scan: the count pass then runs.
+    const bool fused = n != 0 && !aligned_range(w, lo, hi).empty && capacity != 0;
+    uint32_t* seg = nullptr;
+    if (fused) {
+        SSS_TRY(positions_workspace(ctx, n, st));
+        seg = positions_seg_counts(ctx->d_ws, n);
+        SSS_CK(cudaMemsetAsync(seg, 0, positions_seg_count_bytes(n), st));
+    }
+    SSS_TRY(scan_range_impl(ctx, d_packed, n, w, lo, hi, d_bitvec, reinterpret_cast<unsigned long long*>(d_count), false, st,
+                            seg));
+    return positions_impl(ctx, d_bitvec, n, base, d_positions, capacity, nullptr, st, fused);
 }
 
 // One shared scan = build the predicate index, run the scan (which fills the index's interval

@@ -34,7 +34,11 @@ struct CountTarget {
     unsigned long long* result;
     unsigned long long* slot;
     bool accumulate;
+    // scans only: when set (zeroed by the caller), the scan also adds every 1024-word segment's matches to
+    // seg_count[segment] -- the first pass of the position list (positions.cu) without reading the bitvector
+    uint32_t* seg_count = nullptr;
 };
+constexpr int kPosSegShift = 10;  // a position-list segment = 2^10 result words = 32768 codes (positions.cu)
 
 // scan.cu -- fused unpack + range compare -> bitvector (+count)
 cudaError_t launch_scan_range(const Device& dev, const void* packed, uint64_t n, int w, AlignedRange r,
@@ -105,6 +109,10 @@ size_t positions_workspace_bytes(uint64_t n);
 uint32_t positions_epoch_limit();
 cudaError_t launch_positions(const Device& dev, const uint32_t* bitvec, uint64_t n, uint64_t base,
                              unsigned long long* positions, uint64_t capacity, unsigned long long* num,
-                             void* workspace, uint32_t epoch, cudaStream_t stream);
+                             void* workspace, uint32_t epoch, cudaStream_t stream, bool counted = false);
+// the workspace's per-segment match counts: a scan launched with CountTarget::seg_count pointing here (zeroed
+// first) makes launch_positions(..., counted = true) skip its own count pass over the bitvector
+uint32_t* positions_seg_counts(void* workspace, uint64_t n);
+size_t positions_seg_count_bytes(uint64_t n);
 
 }  // namespace sss

@@ -334,17 +334,24 @@ pos_expand_kernel(const uint32_t* __restrict__ bitvec, uint64_t n, uint64_t segm
     flush();
 }
 
+uint32_t* positions_seg_counts(void* workspace, uint64_t n)
+{
+    return reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + pos_groups(n) * 16);
+}
+size_t positions_seg_count_bytes(uint64_t n) { return (size_t)pos_segments(n) * 4; }
+
 cudaError_t launch_positions(const Device& dev, const uint32_t* bitvec, uint64_t n, uint64_t base,
                              unsigned long long* positions, uint64_t capacity, unsigned long long* num,
-                             void* workspace, uint32_t /*epoch*/, cudaStream_t stream)
+                             void* workspace, uint32_t /*epoch*/, cudaStream_t stream, bool counted)
 {
     (void)dev;
     const uint64_t segments = pos_segments(n);
     if (segments == 0) return num ? cudaMemsetAsync(num, 0, sizeof(unsigned long long), stream) : cudaSuccess;
     unsigned long long* group_off = static_cast<unsigned long long*>(workspace);
-    uint32_t* seg_count = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + pos_groups(n) * 16);
+    uint32_t* seg_count = positions_seg_counts(workspace, n);
     const unsigned grid = (unsigned)((segments + kWarps - 1) / kWarps);
-    pos_count_kernel<<<grid, kThreads, 0, stream>>>(bitvec, n, segments, seg_count);
+    // counted: the scan that wrote the bitvector has filled seg_count itself (scan.cu, kSeg)
+    if (!counted) pos_count_kernel<<<grid, kThreads, 0, stream>>>(bitvec, n, segments, seg_count);
     pos_offsets_kernel<<<1, kPosScanThreads, 0, stream>>>(seg_count, segments, group_off, num);
     if (capacity != 0)
         pos_expand_kernel<<<grid, kThreads, 0, stream>>>(bitvec, n, segments, seg_count, group_off, base, positions, capacity);

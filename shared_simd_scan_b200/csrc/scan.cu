@@ -186,50 +186,101 @@ __device__ __forceinline__ void load_group(const uint32_t* buf, uint32_t tg, uin
 
 // One tile.  kChecked = false is the hot path (every block of the tile holds 32 valid codes: no
 // bounds or tail handling, 32-bit indexing); kChecked = true handles the last, ragged tile.
-template <int W, int kMode, bool kChecked>
+template <int W, int kMode, bool kChecked, bool kSeg = false>
 __device__ __forceinline__ uint32_t scan_tile(const uint32_t* buf, const ScanArgs<W>& args, uint32_t rot,
                                               uint32_t* __restrict__ tile_out, uint64_t blocks_left,
-                                              uint32_t tail_bits)
+                                              uint32_t tail_bits, uint32_t* __restrict__ tile_seg = nullptr)
 {
     using P = ScanPlan<W>;
-    uint32_t hits = 0;
+    // kSeg: the matches of every position-list segment (2^kPosSegShift result words) are added to
+    // tile_seg[segment - the tile's first segment], CTA-shared counters that the caller adds to the global
+    // segment counts after the tile's barrier.  A round's 256 * kG blocks and a tile's kBlocksPerTile are
+    // powers of two, so a warp's blocks of a round lie in ONE segment, the same for every warp of the CTA,
+    // known at compile time: one REDUX + one shared-memory atomic per warp and segment (or tile, if shorter),
+    // none when the warp found nothing.  (Global atomics straight from the warps -- 2^20 of them per 2^30
+    // codes, 32 per counter, all concurrent ones within a few cache lines -- cost 60 us per scan.)
+    constexpr int kRoundBlocks = kThreads * P::kG;
+    static_assert(!kSeg || ((kRoundBlocks & (kRoundBlocks - 1)) == 0 && kRoundBlocks <= (1 << kPosSegShift)),
+                  "a round must not straddle position-list segments");
+    uint32_t hits = 0, seg_hits = 0;
 #pragma unroll
     for (int r = 0; r < P::kR; r++) {
         const uint32_t tg = r * kThreads + threadIdx.x;
         const uint32_t b0 = tg * P::kG;  // first block of this group, relative to the tile
-        if (kChecked && b0 >= blocks_left) continue;
-        uint32_t x[P::kG][W];
-        load_group<W>(buf, tg, x, rot);
-        uint32_t res[P::kG];
+        if (!kChecked || b0 < blocks_left) {
+            uint32_t x[P::kG][W];
+            load_group<W>(buf, tg, x, rot);
+            uint32_t res[P::kG];
 #pragma unroll
-        for (int b = 0; b < P::kG; b++) {
-            uint32_t v = eval_block<W, kMode>(x[b], args);
-            if constexpr (P::kRot) v = __funnelshift_l(v, v, rot * (128 / W));
-            if constexpr (kChecked) {
-                if (tail_bits != 0 && b0 + b == blocks_left - 1) v &= (1u << tail_bits) - 1u;
-                if (b0 + b >= blocks_left) v = 0;
+            for (int b = 0; b < P::kG; b++) {
+                uint32_t v = eval_block<W, kMode>(x[b], args);
+                if constexpr (P::kRot) v = __funnelshift_l(v, v, rot * (128 / W));
+                if constexpr (kChecked) {
+                    if (tail_bits != 0 && b0 + b == blocks_left - 1) v &= (1u << tail_bits) - 1u;
+                    if (b0 + b >= blocks_left) v = 0;
+                }
+                if constexpr (kSeg) seg_hits += __popc(v);
+                else hits += __popc(v);
+                res[b] = v;
             }
-            hits += __popc(v);
-            res[b] = v;
-        }
-        uint32_t* dst = tile_out + b0;
-        if (P::kG == 4 && (!kChecked || b0 + 4 <= blocks_left)) {
-            SSS_SCAN_ST(reinterpret_cast<uint4*>(dst), make_uint4(res[0], res[1 % P::kG], res[2 % P::kG], res[3 % P::kG]));
-        } else if (P::kG == 2 && (!kChecked || b0 + 2 <= blocks_left)) {
-            SSS_SCAN_ST(reinterpret_cast<uint2*>(dst), make_uint2(res[0], res[1 % P::kG]));
-        } else {
+            uint32_t* dst = tile_out + b0;
+            if (P::kG == 4 && (!kChecked || b0 + 4 <= blocks_left)) {
+                SSS_SCAN_ST(reinterpret_cast<uint4*>(dst), make_uint4(res[0], res[1 % P::kG], res[2 % P::kG], res[3 % P::kG]));
+            } else if (P::kG == 2 && (!kChecked || b0 + 2 <= blocks_left)) {
+                SSS_SCAN_ST(reinterpret_cast<uint2*>(dst), make_uint2(res[0], res[1 % P::kG]));
+            } else {
 #pragma unroll
-            for (int b = 0; b < P::kG; b++)
-                if (!kChecked || b0 + b < blocks_left) SSS_SCAN_ST(dst + b, res[b]);
+                for (int b = 0; b < P::kG; b++)
+                    if (!kChecked || b0 + b < blocks_left) SSS_SCAN_ST(dst + b, res[b]);
+            }
+        }
+        if constexpr (kSeg) {
+            constexpr int sh = kPosSegShift;
+            const int seg_rel = (r * kRoundBlocks) >> sh;
+            if (r == P::kR - 1 || (((r + 1) * kRoundBlocks) >> sh) != seg_rel) {  // (compile-time per unrolled r)
+                const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, seg_hits);
+                // (explicit red.shared from lane 0: atomicAdd() on shared memory brings a warp-aggregation
+                // preamble of a dozen instructions and a divergent branch)
+                if ((threadIdx.x & 31) == 0)
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(tile_seg + seg_rel)), "r"(c) : "memory");
+                hits += seg_hits;
+                seg_hits = 0;
+            }
         }
     }
     return hits;
 }
 
 // every tile this CTA owns (static round-robin); returns the thread's match count
-template <int W, int kMode>
+// position-list segments a tile covers (tiles shorter than a segment add to the one they lie in)
+template <int W>
+constexpr int kSegsPerTile = ScanPlan<W>::kBlocksPerTile > (1 << kPosSegShift) ? (ScanPlan<W>::kBlocksPerTile >> kPosSegShift) : 1;
+constexpr int kMaxSegsPerTile = 8;
+
+// after the tile's barrier: the CTA's counters of the tile go to the global segment counts and are cleared
+template <int W>
+__device__ __forceinline__ void flush_seg_counts(uint32_t* acc, uint32_t* __restrict__ seg_count, uint64_t tile_block0)
+{
+    static_assert(kSegsPerTile<W> <= kMaxSegsPerTile, "seg_acc rows");
+    // (the last warp's first lanes: thread 0 is busy refilling the ring)
+    const uint32_t t = threadIdx.x - (kThreads - 32);
+    if (t < (uint32_t)kSegsPerTile<W>) {
+        const uint32_t c = acc[t];
+        if (c != 0) {
+            acc[t] = 0;
+            // an explicit RED: atomicAdd() with its result unused came out as ATOMG ..., RZ, and the flushing
+            // thread -- the one that refills the ring -- then sat out an L2 round trip per tile (+30 % per scan)
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(seg_count + (tile_block0 >> kPosSegShift) + t),
+                         "r"(c)
+                         : "memory");
+        }
+    }
+}
+
+template <int W, int kMode, bool kSeg = false>
 __device__ __forceinline__ uint32_t scan_tiles(typename ScanPlan<W>::Ring& ring, const ScanArgs<W>& args, uint64_t n,
-                                               uint32_t* __restrict__ bitvec)
+                                               uint32_t* __restrict__ bitvec, uint32_t* __restrict__ seg_count = nullptr,
+                                               uint32_t (*seg_acc)[kMaxSegsPerTile] = nullptr)
 {
     using P = ScanPlan<W>;
     const uint64_t n_blocks = (n + 31) >> 5;  // result words
@@ -244,29 +295,40 @@ __device__ __forceinline__ uint32_t scan_tiles(typename ScanPlan<W>::Ring& ring,
         const uint32_t* buf = ring.stage_words(iter % P::kStages);
         const uint64_t tile_block0 = tile * (uint64_t)P::kBlocksPerTile;
         uint32_t* tile_out = bitvec + tile_block0;
+        // (two rows of counters: the warps of iteration i + 1 add while row i & 1 is being flushed; row i & 1
+        // is next used by iteration i + 2, behind the barrier of i + 1)
+        uint32_t* tile_seg = kSeg ? seg_acc[iter & 1u] : nullptr;
         if (tile_block0 + P::kBlocksPerTile <= full_blocks) {
-            hits += scan_tile<W, kMode, false>(buf, args, rot, tile_out, 0, 0);
+            hits += scan_tile<W, kMode, false, kSeg>(buf, args, rot, tile_out, 0, 0, tile_seg);
         } else {
-            hits += scan_tile<W, kMode, true>(buf, args, rot, tile_out, n_blocks - tile_block0, tail_bits);
+            hits += scan_tile<W, kMode, true, kSeg>(buf, args, rot, tile_out, n_blocks - tile_block0, tail_bits, tile_seg);
         }
-        ring.release(iter);
+        ring.release(iter);  // (CTA barrier inside)
+        if constexpr (kSeg) flush_seg_counts<W>(tile_seg, seg_count, tile_block0);
     }
     ring.finish();
     return hits;
 }
 
-template <int W, int kMode>
+template <int W, int kMode, bool kSeg>
 __global__ void __launch_bounds__(kThreads, ScanPlan<W>::kCtasPerSm)
 scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, uint64_t n,
                   const __grid_constant__ ScanArgs<W> args, uint32_t* __restrict__ bitvec,
                   unsigned long long* __restrict__ count, unsigned long long* __restrict__ count_slot,
-                  bool accumulate, unsigned long long* __restrict__ tickets)
+                  bool accumulate, unsigned long long* __restrict__ tickets, uint32_t* __restrict__ seg_count)
 {
     using P = ScanPlan<W>;
     extern __shared__ __align__(128) uint8_t smem[];
     typename P::Ring ring(smem, packed, readable_bytes16, tickets);
+    uint32_t (*acc)[kMaxSegsPerTile] = nullptr;
+    if constexpr (kSeg) {
+        __shared__ uint32_t seg_acc[2][kMaxSegsPerTile];
+        if (threadIdx.x < 2 * kMaxSegsPerTile) (&seg_acc[0][0])[threadIdx.x] = 0;
+        __syncthreads();
+        acc = seg_acc;
+    }
     ring.start();
-    const uint32_t hits = scan_tiles<W, kMode>(ring, args, n, bitvec);
+    const uint32_t hits = scan_tiles<W, kMode, kSeg>(ring, args, n, bitvec, seg_count, acc);
     if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
 }
 
@@ -279,11 +341,11 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
 #define SSS_SCAN_DIRECT_MAXW 1
 #endif
 
-template <int W, int kMode>
+template <int W, int kMode, bool kSeg>
 __global__ void __launch_bounds__(kThreads)
 scan_direct_kernel(const void* __restrict__ packed, uint64_t n, const __grid_constant__ ScanArgs<W> args,
                    uint32_t* __restrict__ bitvec, unsigned long long* __restrict__ count,
-                   unsigned long long* __restrict__ count_slot, bool accumulate)
+                   unsigned long long* __restrict__ count_slot, bool accumulate, uint32_t* __restrict__ seg_count)
 {
     using P = ScanPlan<W>;
     const uint64_t n_blocks = (n + 31) >> 5;
@@ -292,11 +354,22 @@ scan_direct_kernel(const void* __restrict__ packed, uint64_t n, const __grid_con
     const uint64_t tile_block0 = blockIdx.x * (uint64_t)P::kBlocksPerTile;
     const uint32_t* buf = static_cast<const uint32_t*>(packed) + tile_block0 * W;
     uint32_t* tile_out = bitvec + tile_block0;
+    uint32_t* tile_seg = nullptr;
+    if constexpr (kSeg) {
+        __shared__ uint32_t seg_acc[kMaxSegsPerTile];
+        if (threadIdx.x < kMaxSegsPerTile) seg_acc[threadIdx.x] = 0;
+        __syncthreads();
+        tile_seg = seg_acc;
+    }
     uint32_t hits;
     if (tile_block0 + P::kBlocksPerTile <= full_blocks)
-        hits = scan_tile<W, kMode, false>(buf, args, 0u, tile_out, 0, 0);
+        hits = scan_tile<W, kMode, false, kSeg>(buf, args, 0u, tile_out, 0, 0, tile_seg);
     else
-        hits = scan_tile<W, kMode, true>(buf, args, 0u, tile_out, n_blocks - tile_block0, tail_bits);
+        hits = scan_tile<W, kMode, true, kSeg>(buf, args, 0u, tile_out, n_blocks - tile_block0, tail_bits, tile_seg);
+    if constexpr (kSeg) {
+        __syncthreads();
+        flush_seg_counts<W>(tile_seg, seg_count, tile_block0);
+    }
     if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
 }
 
@@ -350,16 +423,16 @@ scan_range_dev_kernel(const void* __restrict__ packed, uint64_t readable_bytes16
 
 // ---- launch ---------------------------------------------------------------------------------------
 
-template <int W, int kMode>
-static cudaError_t launch_mode(const Device& dev, const void* packed, uint64_t n, const ScanArgs<W>& args,
-                               uint32_t* bitvec, const CountTarget& ct, cudaStream_t stream)
+template <int W, int kMode, bool kSeg>
+static cudaError_t launch_mode_seg(const Device& dev, const void* packed, uint64_t n, const ScanArgs<W>& args,
+                                   uint32_t* bitvec, const CountTarget& ct, cudaStream_t stream)
 {
     using P = ScanPlan<W>;
     constexpr int smem = P::Ring::kSmemBytes;
     static bool configured[64] = {};
     if (!configured[dev.ordinal & 63]) {
         cudaError_t e =
-            cudaFuncSetAttribute(scan_range_kernel<W, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(scan_range_kernel<W, kMode, kSeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured[dev.ordinal & 63] = true;
     }
@@ -373,14 +446,23 @@ static cudaError_t launch_mode(const Device& dev, const void* packed, uint64_t n
     // starts working at once (cfg 1 in a CUDA graph: 9.1 -> see profiles/r02_bench extras `cfg1`).
     const bool small = tiles <= (uint64_t)dev.scan_direct_tiles * max_ctas;
     if ((W <= SSS_SCAN_DIRECT_MAXW || small) && tiles < (1ull << 31)) {
-        scan_direct_kernel<W, kMode><<<(unsigned)tiles, kThreads, 0, stream>>>(packed, n, args, bitvec, ct.result, ct.slot,
-                                                                             ct.accumulate);
+        scan_direct_kernel<W, kMode, kSeg><<<(unsigned)tiles, kThreads, 0, stream>>>(packed, n, args, bitvec, ct.result,
+                                                                                   ct.slot, ct.accumulate, ct.seg_count);
         return cudaGetLastError();
     }
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    scan_range_kernel<W, kMode><<<grid, kThreads, smem, stream>>>(packed, readable, n, args, bitvec, ct.result, ct.slot,
-                                                                  ct.accumulate, dev.next_tickets());
+    scan_range_kernel<W, kMode, kSeg><<<grid, kThreads, smem, stream>>>(packed, readable, n, args, bitvec, ct.result, ct.slot,
+                                                                        ct.accumulate, dev.next_tickets(), ct.seg_count);
     return cudaGetLastError();
+}
+
+// ct.seg_count set: the variant that also fills the position list's segment counts (sss_scan_range_positions)
+template <int W, int kMode>
+static cudaError_t launch_mode(const Device& dev, const void* packed, uint64_t n, const ScanArgs<W>& args,
+                               uint32_t* bitvec, const CountTarget& ct, cudaStream_t stream)
+{
+    if (ct.seg_count != nullptr) return launch_mode_seg<W, kMode, true>(dev, packed, n, args, bitvec, ct, stream);
+    return launch_mode_seg<W, kMode, false>(dev, packed, n, args, bitvec, ct, stream);
 }
 
 template <int W>

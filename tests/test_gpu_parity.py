@@ -596,6 +596,42 @@ def test_scan_positions_one_call(sss, w):
             assert (host(pos)[:ecnt].astype(np.uint64) == epos).all(), (w, n, lo, hi)
 
 
+@pytest.mark.parametrize("w", ALL_W)
+def test_scan_positions_fused_counts_every_width(scan_path, w):
+    """sss_scan_range_positions lets the SCAN fill the position list's segment counts (scan.cu kSeg: one
+    warp-aggregated atomic per warp and 1024-word segment) instead of a count pass over the bitvector.
+    Every width has its own tile geometry (256 .. 8192 result words per tile, 1 .. 8 rounds), so all 32 are
+    checked against the oracle, on both scan kernels, at sizes around the segment and tile borders."""
+    sss = scan_path
+    m = (1 << w) - 1
+    for n in [1, 32767, 32768 * 8 + 1, 300_007]:
+        codes, packed = column(n, w, seed=950 + w)
+        d_packed = dev(packed)
+        for lo, hi in [(m // 4, m // 2), (int(codes[n // 3]), int(codes[n // 3])), (0, m)]:
+            bv, pos, cnt = sss.scan_positions(d_packed, n, w, lo, hi, base=7)
+            exp, ecnt = B.scan_range(packed, n, w, lo, hi, granule=1)
+            assert (host(bv)[: len(exp)] == exp).all() and int(cnt.item()) == ecnt, (w, n, lo, hi)
+            assert (host(pos)[:ecnt].astype(np.uint64) == B.positions(exp, n, base=7)).all(), (w, n, lo, hi)
+
+
+@pytest.mark.parametrize("w", [2, 3, 4, 6, 9, 11, 13, 16, 17, 23, 32])
+def test_scan_positions_fused_equals_two_calls_long_column(sss, w):
+    """Long columns (the persistent ring kernel with thousands of tiles drawn from the ticket counter): the
+    fused call must give exactly what sss_scan_range followed by sss_positions gives."""
+    m = (1 << w) - 1
+    n = (1 << (29 if w <= 4 else 27)) + 12_345
+    d_packed = sss.generate_packed(n, w, seed=77 + w)
+    for lo, hi in [(m // 4, m // 2), (1 & m, 1 & m)]:
+        bv0, cnt0 = sss.scan(d_packed, n, w, lo, hi)
+        pos0, num0 = sss.positions(bv0, n, base=3, capacity=int(cnt0.item()))
+        bv, pos, cnt = sss.scan_positions(d_packed, n, w, lo, hi, base=3, capacity=int(cnt0.item()))
+        assert int(cnt.item()) == int(cnt0.item()) == int(num0.item())
+        nb = 4 * ((n + 31) // 32)  # (the buffers' padding beyond the result words is never written)
+        assert torch.equal(bv[:nb], bv0[:nb])
+        assert torch.equal(pos[: int(cnt0.item())], pos0[: int(cnt0.item())]), (w, lo, hi)
+        del bv0, pos0, bv, pos
+
+
 def test_positions_many_tiles_and_reuse(sss):
     """The single-pass position list across thousands of look-back tiles, dense and sparse, called
     repeatedly on one context (epoch-tagged tile states: no clearing between launches) and with
