@@ -907,6 +907,14 @@ def calibration(api, timed, peak):
         moved = {"read": nbytes, "write": nbytes, "copy": 2 * nbytes}.get(mode, nbytes + nbytes // ratio)
         rows.append({"mode": mode if mode != "mix" else f"read:write = {ratio}:1", "gb_per_s": round(moved / ms / 1e6, 1),
                      "vs_copy_peak": round(moved / ms / 1e6 / peak, 4)})
+    # the same mixes at the SIZE of the 2^30-code scans at 1-4 bit (128-512 MiB in, 128 MiB out): a 45-100 us
+    # launch pays its ramp and drain, so this -- not the 4 GiB figure -- is what those widths can be held to
+    for w in (1, 2, 3, 4):
+        nb = w << 27
+        ms = launch_ms(lambda: api.calibrate("mix", a, b, nb, w))
+        moved = nb + nb // w
+        rows.append({"mode": f"read:write = {w}:1 at the {w}-bit scan's size ({nb >> 20} MiB in)", "us": round(ms * 1e3, 1),
+                     "gb_per_s": round(moved / ms / 1e6, 1), "vs_copy_peak": round(moved / ms / 1e6 / peak, 4)})
     del a, b
     return rows
 

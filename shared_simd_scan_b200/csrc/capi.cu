@@ -311,6 +311,7 @@ int sss_ctx_create(int device, sss_ctx** out)
     ctx->dev.sm_count = prop.multiProcessorCount;
     ctx->dev.smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* e = std::getenv("SSS_SCAN_DIRECT_TILES")) ctx->dev.scan_direct_tiles = (uint32_t)std::atoi(e);
+    if (const char* e = std::getenv("SSS_PDL")) ctx->dev.pdl = std::atoi(e) != 0;
     for (auto& s : ctx->slots) {
         cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {

@@ -23,6 +23,18 @@ constexpr int kWarps = kThreads / 32;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 
+// Programmatic dependent launch (kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization):
+// pdl_enter() at the very top of a kernel lets the NEXT kernel of the stream be scheduled as this one's CTAs
+// leave, and then waits until the PREVIOUS kernel has completed and its writes are visible.  Nothing before
+// it may touch global memory.  Launched without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter()
+{
+    pdl_trigger();
+    pdl_wait();
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

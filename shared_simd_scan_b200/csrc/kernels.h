@@ -24,6 +24,11 @@ struct Device {
     // in the environment at sss_ctx_create overrides it; 0 = always the persistent ring kernel -- the parity
     // tests run both)
     uint32_t scan_direct_tiles = 8;
+    // scan.cu: launch the ring-less scan kernel with programmatic stream serialization (SSS_PDL=0 in the
+    // environment at sss_ctx_create switches it off): its CTAs are scheduled while the previous kernel drains and
+    // wait in griddepcontrol.wait, at the top of the kernel, until it has completed -- stream order as before,
+    // without the launch gap between back-to-back scans
+    bool pdl = true;
     unsigned long long* next_tickets() const { return ticket_pool + 2 * (size_t)(ticket_cursor++ % kTicketSlots); }
 };
 

@@ -337,8 +337,13 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
 // there the ring's prologue and the persistent CTAs' drain are a visible share of the launch, and a
 // plain grid of short-lived CTAs keeps more of the machine busy at both ends.
 // Measured (profiles/r01_ab_scan_narrow.txt): +5 % at W = 1, nothing at W = 2, 3.
+// End of round 2: the kernel is launched with programmatic stream serialization (pdl_enter, common.cuh), so
+// back-to-back scans lose no launch gap: W = 1 0.886 -> 0.93 of the copy peak (46.3 -> 44.0 us), W = 2 -- now
+// direct as well -- 0.932 -> 0.991 (66.0 -> 62.0 us).  The persistent ring kernel is launched the plain way: with
+// the attribute it gained 1 % at some widths and lost 2-8 % at 3, 5, 11-13 and 17 bit, wherever its CTAs let
+// the next kernel in (profiles/r02_pdl_ab.txt, r02_pdl_ab2.txt).
 #ifndef SSS_SCAN_DIRECT_MAXW
-#define SSS_SCAN_DIRECT_MAXW 1
+#define SSS_SCAN_DIRECT_MAXW 2
 #endif
 
 template <int W, int kMode, bool kSeg>
@@ -348,6 +353,7 @@ scan_direct_kernel(const void* __restrict__ packed, uint64_t n, const __grid_con
                    unsigned long long* __restrict__ count_slot, bool accumulate, uint32_t* __restrict__ seg_count)
 {
     using P = ScanPlan<W>;
+    pdl_enter();
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint64_t full_blocks = n >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
@@ -445,15 +451,23 @@ static cudaError_t launch_mode_seg(const Device& dev, const void* packed, uint64
     // launch, and a plain grid of one short-lived CTA per tile reading straight from global memory / L2
     // starts working at once (cfg 1 in a CUDA graph: 9.1 -> see profiles/r02_bench extras `cfg1`).
     const bool small = tiles <= (uint64_t)dev.scan_direct_tiles * max_ctas;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = stream;
+    cfg.attrs = attr;
     if ((W <= SSS_SCAN_DIRECT_MAXW || small) && tiles < (1ull << 31)) {
-        scan_direct_kernel<W, kMode, kSeg><<<(unsigned)tiles, kThreads, 0, stream>>>(packed, n, args, bitvec, ct.result,
-                                                                                   ct.slot, ct.accumulate, ct.seg_count);
-        return cudaGetLastError();
+        cfg.numAttrs = dev.pdl ? 1 : 0;  // (the ring kernel below: no attribute, see scan_direct_kernel)
+        cfg.gridDim = dim3((unsigned)tiles);
+        return cudaLaunchKernelEx(&cfg, scan_direct_kernel<W, kMode, kSeg>, packed, n, args, bitvec, ct.result, ct.slot,
+                                  ct.accumulate, ct.seg_count);
     }
-    const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    scan_range_kernel<W, kMode, kSeg><<<grid, kThreads, smem, stream>>>(packed, readable, n, args, bitvec, ct.result, ct.slot,
-                                                                        ct.accumulate, dev.next_tickets(), ct.seg_count);
-    return cudaGetLastError();
+    cfg.gridDim = dim3((unsigned)(tiles < max_ctas ? tiles : max_ctas));
+    cfg.dynamicSmemBytes = smem;
+    return cudaLaunchKernelEx(&cfg, scan_range_kernel<W, kMode, kSeg>, packed, readable, n, args, bitvec, ct.result, ct.slot,
+                              ct.accumulate, dev.next_tickets(), ct.seg_count);
 }
 
 // ct.seg_count set: the variant that also fills the position list's segment counts (sss_scan_range_positions)

@@ -28,7 +28,7 @@ def parse_output(data_size, predicate_count, output):
 
 @pytest.mark.parametrize("K", [8, 64])
 def test_cli_sharedscan_feeds_the_reference_scraper(K):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "shared_simd_scan_cli.py"), "40", "1", "sharedscan", str(K)],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "shared_simd_scan_cli.py"), "40", "5", "sharedscan", str(K)],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "first mismatch" not in r.stdout, r.stdout          # the CLI checks its results like check_scan_result
@@ -45,9 +45,14 @@ def test_cli_sharedscan_feeds_the_reference_scraper(K):
     back = list(csv.DictReader(io.StringIO(buf.getvalue())))
     for row in back:
         assert float(row["avg_runtime_ms"]) > 0 and int(row["predicate_count"]) == K
-    by = {row["variant"]: float(row["avg_runtime_ms"]) for row in back}
-    # one pass for K predicates must beat K passes
-    assert by["sse 128, standard"] < by["sse 128, sequential (unrolled)"]
+    # one pass for K predicates must beat K passes (best of the five repetitions each: a 0.1 ms measurement right
+    # after start-up also sees clock ramps and first-launch costs, and back-to-back single scans overlap their
+    # launches since the end of round 2)
+    best = {}
+    for line in r.stdout.splitlines():
+        if line.startswith('*'):
+            best[line[2:].split(': ')[0]] = min(float(x) for x in line.split('[')[1].split(']')[0].split(', '))
+    assert best["sse 128, standard"] < best["sse 128, sequential (unrolled)"], r.stdout
 
 
 @pytest.mark.parametrize("bench", ["scan", "decompression"])
