@@ -59,9 +59,9 @@ def measured_peak():
 
 def captured_traffic():
     """DRAM bytes of the 32 scan launches of one step, from the committed ncu capture
-    (profiles/r02_scan_traffic.json; tools/scan_traffic.py + tools/summarise_traffic.py)."""
+    (profiles/r02_scan_traffic_v2.json; tools/scan_traffic.py + tools/summarise_traffic.py)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r02_scan_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_scan_traffic_v2.json")) as f:
             t = json.load(f)
         return float(t["traffic_per_step"]), float(t["algorithmic_per_step"])
     except Exception:
@@ -596,7 +596,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic if args.logn == 30 else None,
                      "algorithmic_bytes": total_bytes, "peak_source": peak_src,
-                     "traffic_source": "ncu dram bytes of the step's 32 launches, profiles/r02_scan_traffic.json",
+                     "traffic_source": "ncu dram bytes of the step's 32 launches, profiles/r02_scan_traffic_v2.json",
                      "kernel": "sss::scan_range_kernel<W>, the 32 launches of a step (W = 1: scan_direct_kernel); "
                                "bytes = sum n*(w/8+1/8), time = the step's device time in the timed region",
                      "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},

@@ -2,7 +2,7 @@
 """Driver for per-family ncu captures: runs ONE op a few times so that `ncu -k regex:<kernel> -s 2 -c 1`
 profiles a warm launch.
 
-    python tools/ncu_family_driver.py unpack|pack|linear1024|scan|shared:K|linear:K|positions [w] [log2_n]
+    python tools/ncu_family_driver.py unpack|pack|linear1024|scan|scanpos|shared:K|linear:K|positions [w] [log2_n]
 """
 import os
 import sys
@@ -59,6 +59,15 @@ elif op == "positions":
     pos = torch.empty(max(hits, 1), dtype=torch.int64, device="cuda")
     num = torch.empty(1, dtype=torch.int64, device="cuda")
     f = lambda: api.positions(bv, n, capacity=hits, out=pos, num=num)  # noqa: E731
+elif op == "scanpos":  # the fused call: scan (fills the list's segment counts) + group offsets + expansion
+    bv = torch.empty(api.bitvec_bytes(n), dtype=torch.uint8, device="cuda")
+    c1 = torch.empty(1, dtype=torch.int64, device="cuda")
+    sel = float(os.environ.get("SEL", "0.01"))
+    hi_v = max(0, int(sel * (m + 1)) - 1)
+    api.scan(packed, n, w, 0, hi_v, out=bv, count=c1)
+    hits = int(c1.item())
+    pos = torch.empty(max(hits, 1), dtype=torch.int64, device="cuda")
+    f = lambda: api.scan_positions(packed, n, w, 0, hi_v, capacity=hits, out=bv, pos_out=pos, count=c1)  # noqa: E731
 else:
     raise SystemExit("unknown op " + op)
 for _ in range(4):
