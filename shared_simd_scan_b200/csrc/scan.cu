@@ -427,6 +427,61 @@ scan_range_dev_kernel(const void* __restrict__ packed, uint64_t readable_bytes16
     if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
 }
 
+// ... and its ring-less form (one CTA per tile, programmatic launch) for one- and two-bit codes and for short
+// columns, like scan_direct_kernel: a K = 1 shared scan over a short column otherwise pays the ring's prologue.
+template <int W, int kMode>
+__device__ __forceinline__ uint32_t scan_direct_tile(const void* __restrict__ packed, uint64_t n, const ScanArgs<W>& args,
+                                                     uint32_t* __restrict__ bitvec)
+{
+    using P = ScanPlan<W>;
+    const uint64_t n_blocks = (n + 31) >> 5;
+    const uint64_t full_blocks = n >> 5;
+    const uint64_t tile_block0 = blockIdx.x * (uint64_t)P::kBlocksPerTile;
+    const uint32_t* buf = static_cast<const uint32_t*>(packed) + tile_block0 * W;
+    if (tile_block0 + P::kBlocksPerTile <= full_blocks)
+        return scan_tile<W, kMode, false>(buf, args, 0u, bitvec + tile_block0, 0, 0);
+    return scan_tile<W, kMode, true>(buf, args, 0u, bitvec + tile_block0, n_blocks - tile_block0, (uint32_t)(n & 31));
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+scan_direct_dev_kernel(const void* __restrict__ packed, uint64_t n, const uint32_t* __restrict__ d_lo,
+                       const uint32_t* __restrict__ d_hi, uint32_t* __restrict__ bitvec,
+                       unsigned long long* __restrict__ count, unsigned long long* __restrict__ count_slot, bool accumulate)
+{
+    using P = ScanPlan<W>;
+    pdl_enter();
+    const uint32_t lo = __ldg(d_lo);
+    uint32_t hi = __ldg(d_hi);
+    uint32_t hits = 0;
+    if (lo > hi || lo > code_mask(W)) {  // matches nothing (kernel-uniform): this tile's result words are zero
+        const uint64_t n_blocks = (n + 31) >> 5;
+        const uint64_t b0 = blockIdx.x * (uint64_t)P::kBlocksPerTile;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)P::kBlocksPerTile && b0 + i < n_blocks; i += kThreads) bitvec[b0 + i] = 0u;
+    } else {
+        if (hi > code_mask(W)) hi = code_mask(W);
+        ScanArgs<W> args{};
+        if constexpr (W == 1) {
+            args.onebit.flip = (lo == 0 && hi == 0) ? 0xFFFFFFFFu : 0u;
+            args.onebit.all = (lo == 0 && hi == 1) ? 0xFFFFFFFFu : 0u;
+            hits = scan_direct_tile<W, kOneBit>(packed, n, args, bitvec);
+        } else if constexpr (W == 2) {
+            args.bool2 = make_bool2(lo, hi);
+            hits = scan_direct_tile<W, kBool2>(packed, n, args, bitvec);
+        } else if constexpr (P::kSwar) {
+            args.swar = make_swar_consts<W>(lo, hi);
+            hits = args.swar.lo_top ? scan_direct_tile<W, kSwarLoTop1>(packed, n, args, bitvec)
+                                    : scan_direct_tile<W, kSwarLoTop0>(packed, n, args, bitvec);
+        } else {
+            const AlignedRange r = aligned_range(W, lo, hi);
+            args.scalar.lo_al = r.lo_al;
+            args.scalar.span_al = r.span_al;
+            hits = scan_direct_tile<W, kScalar>(packed, n, args, bitvec);
+        }
+    }
+    if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
+}
+
 // ---- launch ---------------------------------------------------------------------------------------
 
 template <int W, int kMode, bool kSeg>
@@ -520,6 +575,20 @@ static cudaError_t launch_w_dev(const Device& dev, const void* packed, uint64_t 
     const uint64_t readable = round_up_u64(n_blocks * (uint64_t)W * 4, 16);
     const uint64_t tiles = (readable + P::kTileBytes - 1) / P::kTileBytes;
     const uint64_t max_ctas = (uint64_t)dev.sm_count * P::kCtasPerSm;
+    const bool small = tiles <= (uint64_t)dev.scan_direct_tiles * max_ctas;
+    if ((W <= SSS_SCAN_DIRECT_MAXW || small) && tiles < (1ull << 31)) {
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)tiles);
+        cfg.blockDim = dim3(kThreads);
+        cfg.stream = stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = dev.pdl ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, scan_direct_dev_kernel<W>, packed, n, d_lo, d_hi, bitvec, ct.result, ct.slot,
+                                  ct.accumulate);
+    }
     const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     scan_range_dev_kernel<W><<<grid, kThreads, smem, stream>>>(packed, readable, n, d_lo, d_hi, bitvec, ct.result,
                                                                ct.slot, ct.accumulate, dev.next_tickets());

@@ -597,6 +597,28 @@ def test_scan_positions_one_call(sss, w):
 
 
 @pytest.mark.parametrize("w", ALL_W)
+def test_single_predicate_shared_scan_both_kernels(scan_path, w):
+    """K = 1: the shared scan IS the scan kernel with its bounds read on the device -- the ring-less kernel for
+    1-2 bit codes and short columns (scan_direct_dev_kernel), the persistent ring kernel otherwise
+    (scan_range_dev_kernel; forced by the `ring` variant of the fixture).  Both layouts, the count, an empty
+    and an out-of-domain predicate, ragged sizes."""
+    sss = scan_path
+    m = (1 << w) - 1
+    for n in [1, 33, 8192 * 3 + 5, 300_007]:
+        codes, packed = column(n, w, seed=400 + w)
+        d_packed = dev(packed)
+        nb = (n + 7) // 8
+        for lo, hi in [(m // 4, m // 2), (int(codes[n // 2]), int(codes[n // 2])), (0, m), (min(3, m), min(3, m) - 1)]:
+            exp, ecnt = B.shared_scan(packed, n, w, [lo], [hi], granule=1)
+            got, cnt = sss.shared_scan(d_packed, n, w, [lo], [hi])
+            assert (host(got)[:, :nb] == exp).all(), (w, n, lo, hi)
+            assert not host(got)[:, nb: 4 * ((n + 31) // 32)].any()
+            assert (host(cnt).astype(np.uint64) == ecnt).all(), (w, n, lo, hi)
+            lin, cnt2 = sss.shared_scan_linear(d_packed, n, w, [lo], [hi])
+            assert (host(lin).reshape(-1)[:nb] == exp[0]).all() and (host(cnt2).astype(np.uint64) == ecnt).all()
+
+
+@pytest.mark.parametrize("w", ALL_W)
 def test_scan_positions_fused_counts_every_width(scan_path, w):
     """sss_scan_range_positions lets the SCAN fill the position list's segment counts (scan.cu kSeg: one
     warp-aggregated atomic per warp and 1024-word segment) instead of a count pass over the bitvector.
