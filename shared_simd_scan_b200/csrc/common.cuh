@@ -101,6 +101,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
+// the same without a cache hint (short columns that a caller scans again and again should stay in L2)
+__device__ __forceinline__ void bulk_g2s_plain(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // 256-bit store (sm_100: STG.E.256): one full 32-byte sector per lane.  p must be 32-byte aligned.
 __device__ __forceinline__ void st_v8_u32(void* p, const uint32_t (&w)[8])
 {

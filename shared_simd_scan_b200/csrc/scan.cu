@@ -346,6 +346,54 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
 #define SSS_SCAN_DIRECT_MAXW 2
 #endif
 
+// The ring-less kernels' tile.  A thread owns W (or kG * W) consecutive words.  Read in place, the lanes of a
+// warp load touch up to 32 different 128-byte lines (128-byte lane stride at 32 bit), and from about 9 bit on
+// the kernel is bound by L1 wavefronts: 2^24 codes inside a CUDA graph took 9.3 / 12.8 / 19.1 us per scan at
+// 17 / 23 / 32 bit.  So from 9 bit on the CTA fetches its tile with ONE bulk copy into shared memory and
+// evaluates it there, conflict-free like the ring's stages (dynamic shared memory: kTileBytes + 16): 7.8 / 8.5 /
+// 8.9 us, 2^22 codes at 32 bit 11.3 -> 4.8 us.  Below 9 bit the lanes' pieces share lines (1-2, 4, 8 bit: the
+// loads are contiguous) and the copy's extra round trip costs more than it saves
+// (profiles/r02_direct_staged_short.txt).
+#ifndef SSS_DIRECT_STAGED_MINW
+#define SSS_DIRECT_STAGED_MINW 9
+#endif
+// (11 bit, the one word-parallel width with scalar loads -- a 44-byte lane stride whose 11 loads re-use the same
+// lines -- stays in place: BASELINE configs[0], 2^24 x 11 bit, measured 6.2 us per scan in place, 6.9 us staged)
+template <int W>
+constexpr bool kDirectStaged = (W >= SSS_DIRECT_STAGED_MINW) && (W != 11);
+template <int W>
+constexpr int kDirectSmemBytes = kDirectStaged<W> ? ScanPlan<W>::kTileBytes + 16 : 0;
+
+template <int W>
+__device__ __forceinline__ const uint32_t* direct_tile_words(const void* __restrict__ packed, uint64_t n, uint32_t& rot)
+{
+    using P = ScanPlan<W>;
+    const uint64_t tile_off = blockIdx.x * (uint64_t)P::kTileBytes;
+    const uint8_t* src = static_cast<const uint8_t*>(packed) + tile_off;
+    if constexpr (!kDirectStaged<W>) {
+        rot = 0;
+        return reinterpret_cast<const uint32_t*>(src);
+    } else {
+        extern __shared__ __align__(128) uint8_t smem[];
+        uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P::kTileBytes);
+        const uint64_t readable = round_up_u64(((n + 31) >> 5) * (uint64_t)W * 4, 16);
+        const uint64_t left = readable - tile_off;
+        const uint32_t bytes = left < (uint64_t)P::kTileBytes ? (uint32_t)left : (uint32_t)P::kTileBytes;
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_g2s_plain(smem, src, bytes, bar);
+        }
+        mbar_wait(bar, 0);
+        rot = rot_chunks<W>();
+        return reinterpret_cast<const uint32_t*>(smem);
+    }
+}
+
 template <int W, int kMode, bool kSeg>
 __global__ void __launch_bounds__(kThreads)
 scan_direct_kernel(const void* __restrict__ packed, uint64_t n, const __grid_constant__ ScanArgs<W> args,
@@ -358,7 +406,8 @@ scan_direct_kernel(const void* __restrict__ packed, uint64_t n, const __grid_con
     const uint64_t full_blocks = n >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const uint64_t tile_block0 = blockIdx.x * (uint64_t)P::kBlocksPerTile;
-    const uint32_t* buf = static_cast<const uint32_t*>(packed) + tile_block0 * W;
+    uint32_t rot;
+    const uint32_t* buf = direct_tile_words<W>(packed, n, rot);
     uint32_t* tile_out = bitvec + tile_block0;
     uint32_t* tile_seg = nullptr;
     if constexpr (kSeg) {
@@ -369,9 +418,9 @@ scan_direct_kernel(const void* __restrict__ packed, uint64_t n, const __grid_con
     }
     uint32_t hits;
     if (tile_block0 + P::kBlocksPerTile <= full_blocks)
-        hits = scan_tile<W, kMode, false, kSeg>(buf, args, 0u, tile_out, 0, 0, tile_seg);
+        hits = scan_tile<W, kMode, false, kSeg>(buf, args, rot, tile_out, 0, 0, tile_seg);
     else
-        hits = scan_tile<W, kMode, true, kSeg>(buf, args, 0u, tile_out, n_blocks - tile_block0, tail_bits, tile_seg);
+        hits = scan_tile<W, kMode, true, kSeg>(buf, args, rot, tile_out, n_blocks - tile_block0, tail_bits, tile_seg);
     if constexpr (kSeg) {
         __syncthreads();
         flush_seg_counts<W>(tile_seg, seg_count, tile_block0);
@@ -437,10 +486,11 @@ __device__ __forceinline__ uint32_t scan_direct_tile(const void* __restrict__ pa
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint64_t full_blocks = n >> 5;
     const uint64_t tile_block0 = blockIdx.x * (uint64_t)P::kBlocksPerTile;
-    const uint32_t* buf = static_cast<const uint32_t*>(packed) + tile_block0 * W;
+    uint32_t rot;
+    const uint32_t* buf = direct_tile_words<W>(packed, n, rot);
     if (tile_block0 + P::kBlocksPerTile <= full_blocks)
-        return scan_tile<W, kMode, false>(buf, args, 0u, bitvec + tile_block0, 0, 0);
-    return scan_tile<W, kMode, true>(buf, args, 0u, bitvec + tile_block0, n_blocks - tile_block0, (uint32_t)(n & 31));
+        return scan_tile<W, kMode, false>(buf, args, rot, bitvec + tile_block0, 0, 0);
+    return scan_tile<W, kMode, true>(buf, args, rot, bitvec + tile_block0, n_blocks - tile_block0, (uint32_t)(n & 31));
 }
 
 template <int W>
@@ -516,6 +566,7 @@ static cudaError_t launch_mode_seg(const Device& dev, const void* packed, uint64
     if ((W <= SSS_SCAN_DIRECT_MAXW || small) && tiles < (1ull << 31)) {
         cfg.numAttrs = dev.pdl ? 1 : 0;  // (the ring kernel below: no attribute, see scan_direct_kernel)
         cfg.gridDim = dim3((unsigned)tiles);
+        cfg.dynamicSmemBytes = kDirectSmemBytes<W>;
         return cudaLaunchKernelEx(&cfg, scan_direct_kernel<W, kMode, kSeg>, packed, n, args, bitvec, ct.result, ct.slot,
                                   ct.accumulate, ct.seg_count);
     }
@@ -586,6 +637,7 @@ static cudaError_t launch_w_dev(const Device& dev, const void* packed, uint64_t 
         cfg.stream = stream;
         cfg.attrs = attr;
         cfg.numAttrs = dev.pdl ? 1 : 0;
+        cfg.dynamicSmemBytes = kDirectSmemBytes<W>;
         return cudaLaunchKernelEx(&cfg, scan_direct_dev_kernel<W>, packed, n, d_lo, d_hi, bitvec, ct.result, ct.slot,
                                   ct.accumulate);
     }
