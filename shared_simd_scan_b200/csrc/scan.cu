@@ -41,6 +41,11 @@ namespace sss {
 #define SSS_SCAN_ST(p, v) __stcs((p), (v))
 #endif
 
+// widths whose scans always take the ring-less kernel (see scan_direct_kernel)
+#ifndef SSS_SCAN_DIRECT_MAXW
+#define SSS_SCAN_DIRECT_MAXW 2
+#endif
+
 enum ScanMode : int { kScalar = 0, kSwarLoTop0 = 1, kSwarLoTop1 = 2, kOneBit = 3, kBool2 = 4 };
 
 template <int W>
@@ -186,7 +191,7 @@ __device__ __forceinline__ void load_group(const uint32_t* buf, uint32_t tg, uin
 
 // One tile.  kChecked = false is the hot path (every block of the tile holds 32 valid codes: no
 // bounds or tail handling, 32-bit indexing); kChecked = true handles the last, ragged tile.
-template <int W, int kMode, bool kChecked, bool kSeg = false>
+template <int W, int kMode, bool kChecked, bool kSeg = false, int kR = ScanPlan<W>::kR>
 __device__ __forceinline__ uint32_t scan_tile(const uint32_t* buf, const ScanArgs<W>& args, uint32_t rot,
                                               uint32_t* __restrict__ tile_out, uint64_t blocks_left,
                                               uint32_t tail_bits, uint32_t* __restrict__ tile_seg = nullptr)
@@ -204,7 +209,7 @@ __device__ __forceinline__ uint32_t scan_tile(const uint32_t* buf, const ScanArg
                   "a round must not straddle position-list segments");
     uint32_t hits = 0, seg_hits = 0;
 #pragma unroll
-    for (int r = 0; r < P::kR; r++) {
+    for (int r = 0; r < kR; r++) {
         const uint32_t tg = r * kThreads + threadIdx.x;
         const uint32_t b0 = tg * P::kG;  // first block of this group, relative to the tile
         if (!kChecked || b0 < blocks_left) {
@@ -237,7 +242,7 @@ __device__ __forceinline__ uint32_t scan_tile(const uint32_t* buf, const ScanArg
         if constexpr (kSeg) {
             constexpr int sh = kPosSegShift;
             const int seg_rel = (r * kRoundBlocks) >> sh;
-            if (r == P::kR - 1 || (((r + 1) * kRoundBlocks) >> sh) != seg_rel) {  // (compile-time per unrolled r)
+            if (r == kR - 1 || (((r + 1) * kRoundBlocks) >> sh) != seg_rel) {  // (compile-time per unrolled r)
                 const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, seg_hits);
                 // (explicit red.shared from lane 0: atomicAdd() on shared memory brings a warp-aggregation
                 // preamble of a dozen instructions and a divergent branch)
@@ -253,18 +258,18 @@ __device__ __forceinline__ uint32_t scan_tile(const uint32_t* buf, const ScanArg
 
 // every tile this CTA owns (static round-robin); returns the thread's match count
 // position-list segments a tile covers (tiles shorter than a segment add to the one they lie in)
-template <int W>
-constexpr int kSegsPerTile = ScanPlan<W>::kBlocksPerTile > (1 << kPosSegShift) ? (ScanPlan<W>::kBlocksPerTile >> kPosSegShift) : 1;
+template <int kBlocksPerTile>
+constexpr int kSegsPerTile = kBlocksPerTile > (1 << kPosSegShift) ? (kBlocksPerTile >> kPosSegShift) : 1;
 constexpr int kMaxSegsPerTile = 8;
 
 // after the tile's barrier: the CTA's counters of the tile go to the global segment counts and are cleared
-template <int W>
+template <int kBlocksPerTile>
 __device__ __forceinline__ void flush_seg_counts(uint32_t* acc, uint32_t* __restrict__ seg_count, uint64_t tile_block0)
 {
-    static_assert(kSegsPerTile<W> <= kMaxSegsPerTile, "seg_acc rows");
+    static_assert(kSegsPerTile<kBlocksPerTile> <= kMaxSegsPerTile, "seg_acc rows");
     // (the last warp's first lanes: thread 0 is busy refilling the ring)
     const uint32_t t = threadIdx.x - (kThreads - 32);
-    if (t < (uint32_t)kSegsPerTile<W>) {
+    if (t < (uint32_t)kSegsPerTile<kBlocksPerTile>) {
         const uint32_t c = acc[t];
         if (c != 0) {
             acc[t] = 0;
@@ -304,7 +309,7 @@ __device__ __forceinline__ uint32_t scan_tiles(typename ScanPlan<W>::Ring& ring,
             hits += scan_tile<W, kMode, true, kSeg>(buf, args, rot, tile_out, n_blocks - tile_block0, tail_bits, tile_seg);
         }
         ring.release(iter);  // (CTA barrier inside)
-        if constexpr (kSeg) flush_seg_counts<W>(tile_seg, seg_count, tile_block0);
+        if constexpr (kSeg) flush_seg_counts<P::kBlocksPerTile>(tile_seg, seg_count, tile_block0);
     }
     ring.finish();
     return hits;
@@ -342,9 +347,6 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
 // direct as well -- 0.932 -> 0.991 (66.0 -> 62.0 us).  The persistent ring kernel is launched the plain way: with
 // the attribute it gained 1 % at some widths and lost 2-8 % at 3, 5, 11-13 and 17 bit, wherever its CTAs let
 // the next kernel in (profiles/r02_pdl_ab.txt, r02_pdl_ab2.txt).
-#ifndef SSS_SCAN_DIRECT_MAXW
-#define SSS_SCAN_DIRECT_MAXW 2
-#endif
 
 // The ring-less kernels' tile.  A thread owns W (or kG * W) consecutive words.  Read in place, the lanes of a
 // warp load touch up to 32 different 128-byte lines (128-byte lane stride at 32 bit), and from about 9 bit on
@@ -361,13 +363,29 @@ scan_range_kernel(const void* __restrict__ packed, uint64_t readable_bytes16, ui
 // lines -- stays in place: BASELINE configs[0], 2^24 x 11 bit, measured 6.2 us per scan in place, 6.9 us staged)
 template <int W>
 constexpr bool kDirectStaged = (W >= SSS_DIRECT_STAGED_MINW) && (W != 11);
+// The ring-less kernels' tile: the plan's at 1-2 bit (long columns: 32 words per thread do best); above -- short
+// columns only -- SSS_DIRECT_ROUNDS rounds per thread (0 = the plan's): a column of a few hundred tiles is ONE
+// wave of CTAs that all load, then all compute, then all store, and smaller tiles might give the waves something
+// to overlap with.  Measured (profiles/r02_direct_rounds.txt): one round per thread helps only where the plan's
+// tile leaves fewer than ~300 CTAs (2^24 codes at 3 / 4 bit: 6.6 -> 4.9 us) and costs 10-90 % elsewhere (2^26 codes
+// at 4 / 8 bit: 7.3 -> 14.1 / 9.7 -> 15.1 us), so the plan's tile stays.
+#ifndef SSS_DIRECT_ROUNDS
+#define SSS_DIRECT_ROUNDS 0
+#endif
 template <int W>
-constexpr int kDirectSmemBytes = kDirectStaged<W> ? ScanPlan<W>::kTileBytes + 16 : 0;
+struct DirectPlan {
+    using P = ScanPlan<W>;
+    static constexpr int kR = (W <= SSS_SCAN_DIRECT_MAXW || SSS_DIRECT_ROUNDS <= 0 || SSS_DIRECT_ROUNDS > P::kR) ? P::kR : SSS_DIRECT_ROUNDS;
+    static constexpr int kBlocksPerTile = kThreads * kR * P::kG;
+    static constexpr int kTileBytes = kBlocksPerTile * W * 4;
+};
+template <int W>
+constexpr int kDirectSmemBytes = kDirectStaged<W> ? DirectPlan<W>::kTileBytes + 16 : 0;
 
 template <int W>
 __device__ __forceinline__ const uint32_t* direct_tile_words(const void* __restrict__ packed, uint64_t n, uint32_t& rot)
 {
-    using P = ScanPlan<W>;
+    using P = DirectPlan<W>;
     const uint64_t tile_off = blockIdx.x * (uint64_t)P::kTileBytes;
     const uint8_t* src = static_cast<const uint8_t*>(packed) + tile_off;
     if constexpr (!kDirectStaged<W>) {
@@ -400,7 +418,7 @@ scan_direct_kernel(const void* __restrict__ packed, uint64_t n, const __grid_con
                    uint32_t* __restrict__ bitvec, unsigned long long* __restrict__ count,
                    unsigned long long* __restrict__ count_slot, bool accumulate, uint32_t* __restrict__ seg_count)
 {
-    using P = ScanPlan<W>;
+    using P = DirectPlan<W>;
     pdl_enter();
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint64_t full_blocks = n >> 5;
@@ -418,12 +436,12 @@ scan_direct_kernel(const void* __restrict__ packed, uint64_t n, const __grid_con
     }
     uint32_t hits;
     if (tile_block0 + P::kBlocksPerTile <= full_blocks)
-        hits = scan_tile<W, kMode, false, kSeg>(buf, args, rot, tile_out, 0, 0, tile_seg);
+        hits = scan_tile<W, kMode, false, kSeg, P::kR>(buf, args, rot, tile_out, 0, 0, tile_seg);
     else
-        hits = scan_tile<W, kMode, true, kSeg>(buf, args, rot, tile_out, n_blocks - tile_block0, tail_bits, tile_seg);
+        hits = scan_tile<W, kMode, true, kSeg, P::kR>(buf, args, rot, tile_out, n_blocks - tile_block0, tail_bits, tile_seg);
     if constexpr (kSeg) {
         __syncthreads();
-        flush_seg_counts<W>(tile_seg, seg_count, tile_block0);
+        flush_seg_counts<P::kBlocksPerTile>(tile_seg, seg_count, tile_block0);
     }
     if (count != nullptr) cta_finish_count(hits, count_slot, count, accumulate);
 }
@@ -482,15 +500,15 @@ template <int W, int kMode>
 __device__ __forceinline__ uint32_t scan_direct_tile(const void* __restrict__ packed, uint64_t n, const ScanArgs<W>& args,
                                                      uint32_t* __restrict__ bitvec)
 {
-    using P = ScanPlan<W>;
+    using P = DirectPlan<W>;
     const uint64_t n_blocks = (n + 31) >> 5;
     const uint64_t full_blocks = n >> 5;
     const uint64_t tile_block0 = blockIdx.x * (uint64_t)P::kBlocksPerTile;
     uint32_t rot;
     const uint32_t* buf = direct_tile_words<W>(packed, n, rot);
     if (tile_block0 + P::kBlocksPerTile <= full_blocks)
-        return scan_tile<W, kMode, false>(buf, args, rot, bitvec + tile_block0, 0, 0);
-    return scan_tile<W, kMode, true>(buf, args, rot, bitvec + tile_block0, n_blocks - tile_block0, (uint32_t)(n & 31));
+        return scan_tile<W, kMode, false, false, P::kR>(buf, args, rot, bitvec + tile_block0, 0, 0);
+    return scan_tile<W, kMode, true, false, P::kR>(buf, args, rot, bitvec + tile_block0, n_blocks - tile_block0, (uint32_t)(n & 31));
 }
 
 template <int W>
@@ -506,8 +524,8 @@ scan_direct_dev_kernel(const void* __restrict__ packed, uint64_t n, const uint32
     uint32_t hits = 0;
     if (lo > hi || lo > code_mask(W)) {  // matches nothing (kernel-uniform): this tile's result words are zero
         const uint64_t n_blocks = (n + 31) >> 5;
-        const uint64_t b0 = blockIdx.x * (uint64_t)P::kBlocksPerTile;
-        for (uint32_t i = threadIdx.x; i < (uint32_t)P::kBlocksPerTile && b0 + i < n_blocks; i += kThreads) bitvec[b0 + i] = 0u;
+        const uint64_t b0 = blockIdx.x * (uint64_t)DirectPlan<W>::kBlocksPerTile;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)DirectPlan<W>::kBlocksPerTile && b0 + i < n_blocks; i += kThreads) bitvec[b0 + i] = 0u;
     } else {
         if (hi > code_mask(W)) hi = code_mask(W);
         ScanArgs<W> args{};
@@ -565,7 +583,7 @@ static cudaError_t launch_mode_seg(const Device& dev, const void* packed, uint64
     cfg.attrs = attr;
     if ((W <= SSS_SCAN_DIRECT_MAXW || small) && tiles < (1ull << 31)) {
         cfg.numAttrs = dev.pdl ? 1 : 0;  // (the ring kernel below: no attribute, see scan_direct_kernel)
-        cfg.gridDim = dim3((unsigned)tiles);
+        cfg.gridDim = dim3((unsigned)((readable + DirectPlan<W>::kTileBytes - 1) / DirectPlan<W>::kTileBytes));
         cfg.dynamicSmemBytes = kDirectSmemBytes<W>;
         return cudaLaunchKernelEx(&cfg, scan_direct_kernel<W, kMode, kSeg>, packed, n, args, bitvec, ct.result, ct.slot,
                                   ct.accumulate, ct.seg_count);
@@ -632,7 +650,7 @@ static cudaError_t launch_w_dev(const Device& dev, const void* packed, uint64_t 
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)tiles);
+        cfg.gridDim = dim3((unsigned)((readable + DirectPlan<W>::kTileBytes - 1) / DirectPlan<W>::kTileBytes));
         cfg.blockDim = dim3(kThreads);
         cfg.stream = stream;
         cfg.attrs = attr;

@@ -14,7 +14,7 @@ peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PE
 for logn in [int(x) for x in sys.argv[1:]] or [24]:
     n = 1 << logn
     out = []
-    for w in (3, 5, 7, 9, 11, 13, 16, 17, 23, 32):
+    for w in [int(x) for x in os.environ.get("WIDTHS", "3,5,7,9,11,13,16,17,23,32").split(",")]:
         col = api.generate_packed(n, w, seed=42 + w)
         bv = torch.empty(api.bitvec_bytes(n), dtype=torch.uint8, device="cuda")
         cnt = torch.empty(1, dtype=torch.int64, device="cuda")
