@@ -654,6 +654,33 @@ def test_scan_positions_fused_equals_two_calls_long_column(sss, w):
         del bv0, pos0, bv, pos
 
 
+@pytest.mark.parametrize("w", [1, 2, 5, 9, 11, 17, 32])
+def test_programmatic_launch_keeps_stream_order(sss, w):
+    """The ring-less scan kernel is launched with programmatic stream serialization: its CTAs may be scheduled
+    while the previous kernel of the stream is still running and must wait (griddepcontrol.wait) before they
+    touch memory.  Here the previous kernel PRODUCES the scan's input -- the compressor writes a new column into
+    the same buffer before every scan, nothing synchronises in between -- so a scan that started early would
+    count the previous column."""
+    n = (1 << 20) + 77
+    m = (1 << w) - 1
+    lo, hi = m // 4, m // 2
+    g = torch.Generator(device="cuda").manual_seed(w)
+    packed = torch.zeros(sss.packed_bytes(n, w), dtype=torch.uint8, device="cuda")
+    bv = torch.empty(sss.bitvec_bytes(n), dtype=torch.uint8, device="cuda")
+    cnt = torch.empty(1, dtype=torch.int64, device="cuda")
+    columns = [torch.randint(0, m + 1, (n,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32) for _ in range(24)]
+    expect = [int(((c.to(torch.int64) & 0xFFFFFFFF >= lo) & (c.to(torch.int64) & 0xFFFFFFFF <= hi)).sum().item()) for c in columns]
+    torch.cuda.synchronize()
+    got = []
+    for c in columns:
+        sss.compress(c, w, out=packed)
+        sss.scan(packed, n, w, lo, hi, out=bv, count=cnt)
+        sss.scan(packed, n, w, lo, hi, out=bv, count=cnt)   # scan after scan: the same count again
+        got.append(cnt.clone())
+    torch.cuda.synchronize()
+    assert [int(x.item()) for x in got] == expect
+
+
 def test_positions_many_tiles_and_reuse(sss):
     """The single-pass position list across thousands of look-back tiles, dense and sparse, called
     repeatedly on one context (epoch-tagged tile states: no clearing between launches) and with
