@@ -310,7 +310,7 @@ def test_shared_scan_clustered_bounds_and_codes(sss, w):
     assert (host(cnt2).astype(np.uint64) == lcnt).all()
 
 
-@pytest.mark.parametrize("w", list(range(12, 31)))
+@pytest.mark.parametrize("w", list(range(12, 33)))
 @pytest.mark.parametrize("K", [1, 5, 8])
 def test_few_predicates_clustered(sss, w, K):
     """K <= 8 at every width around the mask-carrying bucket table (14..28 bit; 12, 13 and 29, 30 take
@@ -337,6 +337,43 @@ def test_few_predicates_clustered(sss, w, K):
     if K > 4:
         lo[3], hi[3] = 7, 3                              # empty
         lo[4], hi[4] = m, m                              # the top code only
+    exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
+    bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi)
+    nb = (n + 7) // 8
+    assert (host(bv)[:, :nb] == exp).all()
+    assert (host(cnt).astype(np.uint64) == ecnt).all()
+    lexp, lcnt = B.shared_scan_linear(packed, n, w, lo, hi, granule=1)
+    lin, cnt2 = sss.shared_scan_linear(dev(packed), n, w, lo, hi)
+    assert (host(lin)[:nb] == lexp).all()
+    assert (host(cnt2).astype(np.uint64) == lcnt).all()
+
+
+@pytest.mark.parametrize("K", [1, 5, 8])
+@pytest.mark.parametrize("w", [27, 28, 29, 30, 31, 32])
+def test_few_predicates_wide_codes_at_the_bounds(sss, w, K):
+    """K <= 8 around the seam between the mask-carrying bucket table (narrow.cu, up to 28 bit: 15 threshold bits
+    in the table word) and the thread-per-block kernel (29-32 bit: 16-19 bits below the bucket bits).  Most codes
+    sit within +-40 of a bound -- equal to a threshold in all but their lowest bits, on both sides -- the rest is
+    uniform; equality predicates, adjacent bounds, the domain's ends; ragged column, both layouts, counts.  (Written
+    for an extension of the table to 29-32 bit with tie patching, which was bit-exact but no faster:
+    profiles/r02_few_wide_experiment.txt.)"""
+    n = 40_009
+    rng = np.random.default_rng(5000 * w + K)
+    m = (1 << w) - 1
+    lo = rng.integers(0, m + 1, size=K, dtype=np.uint64)
+    hi = np.minimum(lo + rng.integers(0, 1 << (w - 6), size=K, dtype=np.uint64), m)
+    lo[0] = hi[0] = lo[0] | 0xF                      # an equality predicate whose low four bits are all ones
+    if K > 2:
+        lo[1], hi[1] = 0, 16                         # starts at the domain's first code
+        lo[2], hi[2] = m - 17, m                     # ends at its last
+    if K > 4:
+        lo[3], hi[3] = min(int(hi[0]) + 1, m), min(int(hi[0]) + 3, m)   # adjacent to predicate 0: thresholds 1 and 4 codes apart
+        lo[4] = hi[4] = (int(lo[4]) >> 4 << 4)       # an equality predicate whose low four bits are zero
+    bounds = np.concatenate([lo, hi]).astype(np.int64)
+    codes = bounds[rng.integers(0, len(bounds), size=n)] + rng.integers(-40, 41, size=n)
+    codes[::7] = rng.integers(0, m + 1, size=len(codes[::7]))
+    codes = np.clip(codes, 0, m).astype(np.uint32)
+    packed = B.pack(codes, w)
     exp, ecnt = B.shared_scan(packed, n, w, lo, hi, granule=1)
     bv, cnt = sss.shared_scan(dev(packed), n, w, lo, hi)
     nb = (n + 7) // 8
