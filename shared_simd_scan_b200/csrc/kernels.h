@@ -107,9 +107,10 @@ cudaError_t launch_unpack_at(const Device& dev, const void* packed, int w, const
 cudaError_t launch_calibrate(const Device& dev, int mode, const void* a, void* b, uint64_t bytes, uint32_t ratio,
                              unsigned long long* sink, cudaStream_t stream);
 
-// positions.cu -- bitvector -> ascending position list (single pass, decoupled look-back).  The
-// workspace must be zero when first used and `epoch` must differ from every epoch the workspace has
-// seen since it was last zeroed (1 .. positions_epoch_limit(); capi.cu counts it per context).
+// positions.cu -- bitvector -> ascending position list in three launches that never wait (count per 4 KB
+// segment, group offsets, ordered expansion).  The workspace holds the group offsets and the segment counts;
+// `epoch` is kept for the C ABI's bookkeeping (capi.cu counts it per context; the kernels carry no state
+// between launches).
 size_t positions_workspace_bytes(uint64_t n);
 uint32_t positions_epoch_limit();
 cudaError_t launch_positions(const Device& dev, const uint32_t* bitvec, uint64_t n, uint64_t base,
