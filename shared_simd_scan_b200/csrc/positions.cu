@@ -102,6 +102,7 @@ __device__ __forceinline__ uint32_t popc4(const uint4& a) { return __popc(a.x) +
 __global__ void __launch_bounds__(kThreads)
 pos_count_kernel(const uint32_t* __restrict__ bitvec, uint64_t n, uint64_t segments, uint32_t* __restrict__ seg_count)
 {
+    pdl_enter();  // (launched with programmatic stream serialization, like the two kernels below: common.cuh)
     const uint64_t n_words = (n + 31) >> 5;
     const uint32_t tail_bits = (uint32_t)(n & 31);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(kPosScanThreads)
 pos_offsets_kernel(const uint32_t* __restrict__ seg_count, uint64_t segments, unsigned long long* __restrict__ group_off,
                    unsigned long long* __restrict__ num)
 {
+    pdl_enter();
     __shared__ unsigned long long warp_sum[kPosScanThreads / 32];
     __shared__ unsigned long long carry;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -182,6 +184,7 @@ pos_expand_kernel(const uint32_t* __restrict__ bitvec, uint64_t n, uint64_t segm
                   const uint32_t* __restrict__ seg_count, const unsigned long long* __restrict__ group_off, uint64_t base,
                   unsigned long long* __restrict__ positions, uint64_t capacity)
 {
+    pdl_enter();
     __shared__ __align__(16) uint16_t stage[kWarps][kPosStage];
     __shared__ uint8_t piece_id[kWarps][kPosRounds * 32];
     const uint64_t n_words = (n + 31) >> 5;
@@ -344,18 +347,39 @@ cudaError_t launch_positions(const Device& dev, const uint32_t* bitvec, uint64_t
                              unsigned long long* positions, uint64_t capacity, unsigned long long* num,
                              void* workspace, uint32_t /*epoch*/, cudaStream_t stream, bool counted)
 {
-    (void)dev;
     const uint64_t segments = pos_segments(n);
     if (segments == 0) return num ? cudaMemsetAsync(num, 0, sizeof(unsigned long long), stream) : cudaSuccess;
     unsigned long long* group_off = static_cast<unsigned long long*>(workspace);
     uint32_t* seg_count = positions_seg_counts(workspace, n);
     const unsigned grid = (unsigned)((segments + kWarps - 1) / kWarps);
+    // the three launches of a list are 5-60 us each: their CTAs are scheduled while the previous kernel drains
+    // (programmatic stream serialization; every kernel waits in pdl_enter() before it touches memory)
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = dev.pdl ? 1 : 0;
+    cudaError_t e = cudaSuccess;
     // counted: the scan that wrote the bitvector has filled seg_count itself (scan.cu, kSeg)
-    if (!counted) pos_count_kernel<<<grid, kThreads, 0, stream>>>(bitvec, n, segments, seg_count);
-    pos_offsets_kernel<<<1, kPosScanThreads, 0, stream>>>(seg_count, segments, group_off, num);
-    if (capacity != 0)
-        pos_expand_kernel<<<grid, kThreads, 0, stream>>>(bitvec, n, segments, seg_count, group_off, base, positions, capacity);
-    return cudaGetLastError();
+    if (!counted) {
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        e = cudaLaunchKernelEx(&cfg, pos_count_kernel, bitvec, n, segments, seg_count);
+        if (e != cudaSuccess) return e;
+    }
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(kPosScanThreads);
+    e = cudaLaunchKernelEx(&cfg, pos_offsets_kernel, (const uint32_t*)seg_count, segments, group_off, num);
+    if (e != cudaSuccess) return e;
+    if (capacity != 0) {
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        e = cudaLaunchKernelEx(&cfg, pos_expand_kernel, bitvec, n, segments, (const uint32_t*)seg_count,
+                               (const unsigned long long*)group_off, base, positions, capacity);
+    }
+    return e;
 }
 
 }  // namespace sss
