@@ -35,6 +35,11 @@
 // stage out with consecutive 8-byte stores.  A round with more than half of its bits set skips the
 // stage: the warp takes its words one at a time, lane b owns bit b and stores at the rank of its bit.
 //
+// sss_scan_range_positions skips the first kernel: the scan that writes the bitvector adds every segment's
+// matches to seg_count itself (scan.cu, kSeg; launch_positions(..., counted = true)).  The three kernels are
+// launched with programmatic stream serialization (pdl_enter, common.cuh): 5-60 us launches whose gaps showed
+// (sss_positions at 0.1 % selectivity 53.9 -> 47.7 us, profiles/r02_pos_pdl.txt).
+//
 // Algorithmic bytes: n/8 (bitvector, counted once) + 8 per match.
 #include "common.cuh"
 #include "kernels.h"
